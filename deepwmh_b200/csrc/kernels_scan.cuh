@@ -1,0 +1,212 @@
+// HBM-bound kernels of the path: masked z-score, fused norm+head+softmax, mirror/Gaussian
+// overlap-add aggregation, finalize (divide + argmax), small vector helpers.
+// Reference semantics: SURVEY.md section 8a rows a2, a11, a12 (nnU-Net v1, un-vendored).
+#pragma once
+#include "common.cuh"
+
+namespace dwmh {
+
+// ---------------------------------------------------------------------------------------------
+// a2  z-score.  Pass 1: {sum, sum of squares, count} over the mask in fp64 (12 B/voxel total with
+// pass 2: read, read, write).  128-bit coalesced loads, grid = multiple of the SM count.
+// mask_mode 0: all voxels; 1: seg[i] >= 0; 2: vol[i] != 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zscore_reduce_kernel(const float* __restrict__ vol,
+                                                            const int8_t* __restrict__ seg, int64_t n,
+                                                            int mask_mode, double* __restrict__ acc) {
+  double s = 0.0, ss = 0.0, cnt = 0.0;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const float4* v4 = reinterpret_cast<const float4*>(vol);
+  const char4* s4 = reinterpret_cast<const char4*>(seg);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ld_stream_f4(v4 + i);
+    bool m0 = true, m1 = true, m2 = true, m3 = true;
+    if (mask_mode == 1) { const char4 g = s4[i]; m0 = g.x >= 0; m1 = g.y >= 0; m2 = g.z >= 0; m3 = g.w >= 0; }
+    else if (mask_mode == 2) { m0 = v.x != 0.f; m1 = v.y != 0.f; m2 = v.z != 0.f; m3 = v.w != 0.f; }
+    // fp32 partial of 4 then fp64: keeps the DFMA count at 1/4 of the element count
+    const float a = m0 ? v.x : 0.f, b = m1 ? v.y : 0.f, c = m2 ? v.z : 0.f, d = m3 ? v.w : 0.f;
+    s += (double)a + (double)b + (double)c + (double)d;
+    ss += (double)a * a + (double)b * b + (double)c * c + (double)d * d;
+    cnt += (double)((int)m0 + (int)m1 + (int)m2 + (int)m3);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {          // tail (n % 4)
+    for (int64_t i = n4 << 2; i < n; ++i) {
+      const float v = vol[i];
+      const bool m = mask_mode == 0 ? true : (mask_mode == 1 ? seg[i] >= 0 : v != 0.f);
+      if (m) { s += v; ss += (double)v * v; cnt += 1.0; }
+    }
+  }
+  s = warp_sum_d(s); ss = warp_sum_d(ss); cnt = warp_sum_d(cnt);
+  __shared__ double sh[3][8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = s; sh[1][w] = ss; sh[2][w] = cnt; }
+  __syncthreads();
+  if (w == 0) {
+    s = l < 8 ? sh[0][l] : 0.0; ss = l < 8 ? sh[1][l] : 0.0; cnt = l < 8 ? sh[2][l] : 0.0;
+    s = warp_sum_d(s); ss = warp_sum_d(ss); cnt = warp_sum_d(cnt);
+    if (l == 0) { atomicAdd(acc + 0, s); atomicAdd(acc + 1, ss); atomicAdd(acc + 2, cnt); }
+  }
+}
+
+__device__ __forceinline__ void zscore_stats(const double* acc, float& mean, float& denom) {
+  const double cnt = acc[2] > 0.0 ? acc[2] : 1.0;
+  const double m = acc[0] / cnt;
+  double var = acc[1] / cnt - m * m;
+  var = var > 0.0 ? var : 0.0;
+  mean = (float)m;
+  denom = (float)sqrt(var) + 1e-8f;     // fp32 add, as numpy does with a float32 scalar
+}
+
+__global__ void __launch_bounds__(256) zscore_apply_kernel(float* __restrict__ vol, const int8_t* __restrict__ seg,
+                                                           int64_t n, int mask_mode, const double* __restrict__ acc) {
+  float mean, denom;
+  zscore_stats(acc, mean, denom);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  float4* v4 = reinterpret_cast<float4*>(vol);
+  const char4* s4 = reinterpret_cast<const char4*>(seg);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = v4[i];
+    bool m0 = true, m1 = true, m2 = true, m3 = true;
+    if (mask_mode == 1) { const char4 g = s4[i]; m0 = g.x >= 0; m1 = g.y >= 0; m2 = g.z >= 0; m3 = g.w >= 0; }
+    else if (mask_mode == 2) { m0 = v.x != 0.f; m1 = v.y != 0.f; m2 = v.z != 0.f; m3 = v.w != 0.f; }
+    v.x = m0 ? (v.x - mean) / denom : 0.f;
+    v.y = m1 ? (v.y - mean) / denom : 0.f;
+    v.z = m2 ? (v.z - mean) / denom : 0.f;
+    v.w = m3 ? (v.w - mean) / denom : 0.f;
+    v4[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t i = n4 << 2; i < n; ++i) {
+      const float v = vol[i];
+      const bool m = mask_mode == 0 ? true : (mask_mode == 1 ? seg[i] >= 0 : v != 0.f);
+      vol[i] = m ? (v - mean) / denom : 0.f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head: InstanceNorm+LeakyReLU of the last decoder conv applied on load, 1x1x1 conv to 2 logits
+// (seg_outputs[-1], no bias), softmax over classes (inference_apply_nonlin).  One thread per voxel,
+// grid.y = sample.  y: [n][C/8][V][8] raw conv output; probs: [n][2][V] fp32.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) head_softmax_kernel(const T* __restrict__ y, NormParams np,
+                                                           const float* __restrict__ w_head,   // [2][C]
+                                                           float* __restrict__ probs, int C, int64_t V) {
+  extern __shared__ float sm[];          // a[C], b[C], w0[C], w1[C]
+  float* sa = sm; float* sb = sm + C; float* w0 = sm + 2 * C; float* w1 = sm + 3 * C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 1.f, b = 0.f;
+    if (np.sums) norm_coeffs(np, n, C, c, a, b);
+    sa[c] = a; sb[c] = b; w0[c] = w_head[c]; w1[c] = w_head[C + c];
+  }
+  __syncthreads();
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const uint4* yp = reinterpret_cast<const uint4*>(y) + (size_t)n * (C >> 3) * V + v;
+  float l0 = 0.f, l1 = 0.f;
+  for (int cc = 0; cc < (C >> 3); ++cc) {
+    float f[8];
+    unpack8<T>(ld_stream(yp + (size_t)cc * V), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cc * 8 + j;
+      const float x = np.sums ? lrelu(fmaf(sa[c], f[j], sb[c])) : f[j];
+      l0 = fmaf(w0[c], x, l0);
+      l1 = fmaf(w1[c], x, l1);
+    }
+  }
+  const float m = fmaxf(l0, l1);
+  const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+  const float s = e0 + e1;
+  probs[((size_t)n * 2 + 0) * V + v] = e0 / s;
+  probs[((size_t)n * 2 + 1) * V + v] = e1 / s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a11/a12  One tile: result = sum_m (1/M) * unflip_m(p_m); result *= gaussian; agg[:, tile] += result;
+// wgt[tile] += gaussian.  Same fp32 operation order as the reference.  Tiles are aggregated by
+// consecutive launches on one stream, so the overlap-add is deterministic (no atomics).
+// probs: [M][2][P] for this tile; metas[m].flip gives the mirror of sample m.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) aggregate_tile_kernel(const float* __restrict__ probs,
+                                                             const SampleMeta* __restrict__ metas, int M,
+                                                             const float* __restrict__ gauss,   // [P] or nullptr
+                                                             float* __restrict__ agg, float* __restrict__ wgt,
+                                                             int px, int py, int pz, int X, int Y, int Z) {
+  const int64_t P = (int64_t)px * py * pz;
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= P) return;
+  const int k = (int)(v % pz);
+  const int j = (int)((v / pz) % py);
+  const int i = (int)(v / ((int64_t)pz * py));
+  const float inv = 1.0f / (float)M;
+  float r0 = 0.f, r1 = 0.f;
+  for (int m = 0; m < M; ++m) {
+    const int f = metas[m].flip;
+    const int kk = (f & 1) ? pz - 1 - k : k;
+    const int jj = (f & 2) ? py - 1 - j : j;
+    const int ii = (f & 4) ? px - 1 - i : i;
+    const int64_t src = ((int64_t)ii * py + jj) * pz + kk;
+    r0 += inv * probs[((size_t)m * 2 + 0) * P + src];
+    r1 += inv * probs[((size_t)m * 2 + 1) * P + src];
+  }
+  const float g = gauss ? gauss[v] : 1.0f;
+  if (gauss) { r0 *= g; r1 *= g; }
+  const int64_t V = (int64_t)X * Y * Z;
+  const int64_t dst = ((int64_t)(metas[0].ox + i) * Y + (metas[0].oy + j)) * Z + (metas[0].oz + k);
+  agg[dst] += r0;
+  agg[V + dst] += r1;
+  wgt[dst] += g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a12 tail: class_probabilities = agg / wgt; seg = argmax (first maximum).  21 B/voxel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ agg, const float* __restrict__ wgt,
+                                                       float* __restrict__ softmax_out, uint8_t* __restrict__ seg,
+                                                       int64_t V) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += stride) {
+    const float w = wgt[i];
+    const float p0 = agg[i] / w, p1 = agg[V + i] / w;
+    if (softmax_out) { softmax_out[i] = p0; softmax_out[V + i] = p1; }
+    if (seg) seg[i] = p1 > p0 ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ acc, const float* __restrict__ x, float alpha, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc[i] = fmaf(alpha, x[i], acc[i]);
+}
+
+__global__ void __launch_bounds__(256) argmax2_kernel(const float* __restrict__ p, uint8_t* __restrict__ seg, int64_t V) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += stride) seg[i] = p[V + i] > p[i] ? 1 : 0;
+}
+
+// chunked T [n][C/8][V][8] -> fp32 NCDHW (debug / layer-level parity tests), optional norm+lrelu
+template <typename T>
+__global__ void __launch_bounds__(256) unpack_layer_kernel(const T* __restrict__ y, NormParams np, float* __restrict__ out,
+                                                           int N, int C, int64_t V) {
+  const int64_t total = (int64_t)N * (C >> 3) * V;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t v = i % V;
+    const int cc = (int)((i / V) % (C >> 3));
+    const int n = (int)(i / (V * (C >> 3)));
+    float f[8];
+    unpack8<T>(reinterpret_cast<const uint4*>(y)[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = f[j];
+      if (np.sums) { float a, b; norm_coeffs(np, n, C, cc * 8 + j, a, b); x = lrelu(fmaf(a, x, b)); }
+      out[((size_t)n * C + cc * 8 + j) * V + v] = x;
+    }
+  }
+}
+
+}  // namespace dwmh

@@ -1,0 +1,129 @@
+/* deepwmh_b200.h -- C ABI of the B200-native DeepWMH / nnU-Net 3d_fullres inference path.
+ *
+ * The reference (lchdl/DeepWMH) reaches this path through a process boundary:
+ *   deepwmh/main/predict.py:153-156            run_shell('nnUNet_predict -i .. -o .. -tr nnUNetTrainerV2 ...')
+ *   deepwmh/pipeline/DCNN_multistage.py:331-344,531-535   (same CLI, --save_softmax / --disable_tta)
+ * and, inside that process, through the Python predictor surface of the un-vendored nnunet fork
+ *   nnUNetTrainerV2.predict_preprocessed_data_return_seg_and_softmax / SegmentationNetwork.predict_3D
+ * (SURVEY.md section 8a rows a6/a7).  There is no FFI in the reference for it; these entry points
+ * are what a ctypes binding placed at that seam binds (INTEGRATION.md shows the stub).
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure; dwmh_last_error() gives
+ * the thread-local message.  One dwmh_ctx per GPU, not re-entrant; distinct contexts are
+ * independent.  Device pointers are plain CUDA device addresses owned by the caller; `stream` is
+ * a cudaStream_t passed as void* (NULL = default stream).  Volumes are C-ordered [X][Y][Z]
+ * (Z fastest), exactly the (c, x, y, z) numpy arrays nnU-Net hands to predict_3D with c == 1.
+ * No torch types, no exceptions and no Python objects cross this line.
+ */
+#ifndef DEEPWMH_B200_H_
+#define DEEPWMH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DWMH_MAX_POOL 7
+
+typedef struct dwmh_ctx dwmh_ctx;
+
+/* Generic_UNet hyper-parameters, i.e. what nnUNetTrainerV2.process_plans reads from plans.pkl
+ * (SURVEY.md Appendix A1/A6).  Replaces nnUNetTrainerV2.initialize_network [U]. */
+typedef struct dwmh_net_desc {
+  int32_t in_channels;                        /* plans['num_modalities']; only 1 is supported        */
+  int32_t num_classes;                        /* plans['num_classes'] + 1; only 2 is supported       */
+  int32_t base_num_features;                  /* 32                                                  */
+  int32_t max_num_features;                   /* 320                                                 */
+  int32_t num_pool;                           /* len(pool_op_kernel_sizes)                           */
+  int32_t patch_size[3];                      /* plans_per_stage[..]['patch_size']  (x, y, z)        */
+  int32_t pool_op_kernel_sizes[DWMH_MAX_POOL][3];      /* each entry 1 or 2                          */
+  int32_t conv_kernel_sizes[DWMH_MAX_POOL + 1][3];     /* each entry 1 or 3                          */
+  int32_t act_dtype;                          /* 0 = fp16 operands/storage (default), 1 = bf16       */
+  int32_t max_batch;                          /* patch forwards kept in flight (multiple of 8), 0 = default */
+} dwmh_net_desc;
+
+const char* dwmh_last_error(void);
+int dwmh_version(void);
+
+/* --- life cycle (replaces load_model_and_checkpoint_files + trainer.initialize(False)) ---------- */
+int dwmh_create(dwmh_ctx** out, int device, const dwmh_net_desc* desc);
+int dwmh_destroy(dwmh_ctx* ctx);
+
+/* trainer.load_checkpoint_ram: one call per state_dict entry, nnU-Net key names
+ * ("conv_blocks_context.0.blocks.0.conv.weight", "tu.3.weight", "seg_outputs.4.weight", ...),
+ * fp32 host data in PyTorch layout.  Unknown keys of the deep-supervision heads 0..num_pool-2 are
+ * accepted and ignored (discarded at inference).  dwmh_commit_weights repacks to device layouts and
+ * fails if a required tensor is missing. */
+int dwmh_set_weight(dwmh_ctx* ctx, const char* nnunet_key, const float* data, const int64_t* shape, int32_t ndim);
+int dwmh_commit_weights(dwmh_ctx* ctx);
+
+/* --- a2: GenericPreprocessor.resample_and_normalize, non-CT scheme [U] -------------------------
+ * In place on a device fp32 volume of n voxels.
+ * mask_mode 0: use_mask_for_norm False -> statistics over all voxels, all voxels normalised.
+ * mask_mode 1: mask = (seg[i] >= 0), seg = device int8 array (nnU-Net's nonzero mask); outside -> 0.
+ * mask_mode 2: mask = (vol[i] != 0)   (the benchmark's definition).
+ * x = (x - mean) / (std + 1e-8), population std.  stats_out (host, may be NULL) receives {mean, std, count}. */
+int dwmh_zscore(dwmh_ctx* ctx, float* vol_dev, const int8_t* seg_dev, int64_t n, int32_t mask_mode,
+                double* stats_out, void* stream);
+
+/* --- a8/a9 host helpers -------------------------------------------------------------------------
+ * _compute_steps_for_sliding_window: writes up to max_steps entries per axis, returns counts.
+ * _get_gaussian(patch, 1/8): closed form of scipy's separable filter of a unit impulse. */
+int dwmh_compute_steps(const int32_t patch[3], const int32_t image[3], double step_size,
+                       int32_t* steps_x, int32_t* steps_y, int32_t* steps_z, int32_t max_steps, int32_t counts[3]);
+int dwmh_gaussian_map(const int32_t patch[3], double sigma_scale, float* out_host);
+/* Optional: install a caller-computed importance map (host fp32 [px][py][pz]) instead of the closed form. */
+int dwmh_set_importance_map(dwmh_ctx* ctx, const float* map_host);
+
+/* --- a7/a11/a12: SegmentationNetwork.predict_3D, tiled branch -----------------------------------
+ * vol_dev: normalised fp32 [X][Y][Z], each extent >= patch (caller pads, a10).
+ * Accumulates into agg_dev fp32 [2][X][Y][Z] and wgt_dev fp32 [X][Y][Z] (caller zero-initialises):
+ *   agg[:, tile] += gaussian * sum_m (1/M) unflip_m(softmax(net(flip_m(tile)))),  wgt[tile] += gaussian
+ * for the tiles with linear index in [tile_begin, tile_end) in x-outer / y / z-inner order
+ * (tile_end < 0 = all).  mirror_axes_mask: bit a set = axis a in mirror_axes; do_mirroring = 0 -> M = 1.
+ * use_gaussian = 0 (or a single tile) -> weights of 1.  Tile-sharded multi-GPU runs reduce agg and
+ * wgt across ranks between this call and dwmh_finalize. */
+int dwmh_predict_3d(dwmh_ctx* ctx, const float* vol_dev, int32_t X, int32_t Y, int32_t Z,
+                    double step_size, int32_t do_mirroring, int32_t mirror_axes_mask, int32_t use_gaussian,
+                    float* agg_dev, float* wgt_dev, int32_t tile_begin, int32_t tile_end, void* stream);
+
+/* class_probabilities = agg / wgt ; seg = argmax over classes (first maximum wins).
+ * softmax_dev fp32 [2][X][Y][Z] (may alias agg_dev), seg_dev uint8 [X][Y][Z]; either may be NULL. */
+int dwmh_finalize(dwmh_ctx* ctx, const float* agg_dev, const float* wgt_dev, float* softmax_dev,
+                  uint8_t* seg_dev, int32_t X, int32_t Y, int32_t Z, void* stream);
+
+/* a13 ensemble: acc += softmax / k  (k-model mean of predict_cases), n floats. */
+int dwmh_axpy(dwmh_ctx* ctx, float* acc_dev, const float* x_dev, float alpha, int64_t n, void* stream);
+int dwmh_argmax2(dwmh_ctx* ctx, const float* softmax_dev, uint8_t* seg_dev, int64_t nvox, void* stream);
+
+/* --- a6 end to end with HOST buffers (what predict_preprocessed_data_return_seg_and_softmax does):
+ * raw fp32 volume [X][Y][Z] in host memory -> (optional z-score, mask_mode as above, <0 = skip)
+ * -> tiled prediction -> host softmax fp32 [2][X][Y][Z] and seg uint8 [X][Y][Z].  H2D/D2H inside. */
+int dwmh_predict_volume_host(dwmh_ctx* ctx, const float* vol_host, int32_t X, int32_t Y, int32_t Z,
+                             int32_t zscore_mask_mode, double step_size, int32_t do_mirroring,
+                             int32_t mirror_axes_mask, int32_t use_gaussian,
+                             float* softmax_host, uint8_t* seg_host, void* stream);
+
+/* --- test / profiling hooks ----------------------------------------------------------------------
+ * Generic_UNet.forward + softmax on n patches: patches_dev fp32 [n][px][py][pz] -> probs_dev fp32 [n][2][px][py][pz]. */
+int dwmh_forward_patches(dwmh_ctx* ctx, const float* patches_dev, int32_t n, float* probs_dev, void* stream);
+/* Copy the (normalised, activated) output of layer `layer_index` of the last forward, converted to
+ * fp32 NCDHW, into out_dev (capacity in floats); dims_out = {n, c, d, h, w}.  Layer order = execution order. */
+int dwmh_debug_layer_output(dwmh_ctx* ctx, int32_t layer_index, float* out_dev, int64_t capacity, int32_t dims_out[5], void* stream);
+int dwmh_num_layers(dwmh_ctx* ctx);
+/* Kernel variant used by a layer: 0 = direct (CUDA cores), 1 = tcgen05 implicit GEMM. */
+int dwmh_layer_kernel_kind(dwmh_ctx* ctx, int32_t layer_index);
+/* Force the generic kernels everywhere (1) or restore automatic selection (0) - for cross-checking. */
+int dwmh_set_force_generic(dwmh_ctx* ctx, int32_t on);
+/* Counters since creation: kernels launched by this library, conv FLOPs issued. */
+int dwmh_get_counters(dwmh_ctx* ctx, int64_t* kernel_launches, double* conv_flops);
+/* Device time (ms, CUDA events on `stream`) the last dwmh_predict_3d spent per stage:
+ * out[0]=conv stack, out[1]=head+aggregate.  Only filled when profiling was enabled (adds syncs). */
+int dwmh_set_stage_timing(dwmh_ctx* ctx, int32_t on);
+int dwmh_get_stage_timing(dwmh_ctx* ctx, float out_ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPWMH_B200_H_ */
