@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "common.cuh"
@@ -46,10 +47,23 @@ struct TcKParams {
   int C0, C1, Cout, CB, KC, nkc, nkc0;
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
   int SA, NB, resident, R, fmt;
+  unsigned long long* prof;   // dbg & 8: per-role wait/total cycle counters
+  int dbg;            // profiling knobs (env DWMH_TC_DEBUG): 1 = no activation TMA, 2 = no MMA, 4 = no epilogue stores
   uint32_t a_stage_bytes, b_tile_bytes, off_b, off_bar;
 };
 
-template <typename T>
+// Ring-buffer cursor without div/mod.
+struct RingPos {
+  uint32_t idx = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n) { if (++idx == n) { idx = 0; phase ^= 1; } }
+};
+
+#define DWMH_TIMED_WAIT(acc, ...) do { if (prof_on) { const long long t__ = clock64(); __VA_ARGS__; acc += clock64() - t__; } else { __VA_ARGS__; } } while (0)
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+// KSTEPS = KC/16 (UMMA K steps per channel chunk); SMALL_CB: CB <= 32 -> per-thread running statistics.
+template <typename T, int KSTEPS, bool SMALL_CB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const TcKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -64,15 +78,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int n = wi;
   const int h0 = th * TC_TH, w0 = tw * TC_TW;
   const int z_lo = zb * p.ZB, z_end = min(p.D, z_lo + p.ZB);
-  const int SA = p.SA, NB = p.NB, R = p.R, CB = p.CB;
+  const uint32_t SA = p.SA, NB = p.NB, R = p.R, CB = p.CB;
 
   const uint32_t bar = smem_base + p.off_bar;
-  auto a_full = [&](int s) { return bar + 8u * s; };
-  auto a_empty = [&](int s) { return bar + 8u * (SA + s); };
-  auto b_full = [&](int s) { return bar + 8u * (2 * SA + s); };
-  auto b_empty = [&](int s) { return bar + 8u * (2 * SA + NB + s); };
-  auto acc_full = [&](int s) { return bar + 8u * (2 * SA + 2 * NB + s); };
-  auto acc_empty = [&](int s) { return bar + 8u * (2 * SA + 2 * NB + R + s); };
+  const uint32_t a_full = bar, a_empty = bar + 8u * SA, b_full = bar + 16u * SA, b_empty = b_full + 8u * NB;
+  const uint32_t acc_full = b_empty + 8u * NB, acc_empty = acc_full + 8u * R;
   const uint32_t nbar = 2 * SA + 2 * NB + 2 * R;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * nbar);
   float* s_stat = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar + 16);       // [2][CB]
@@ -80,145 +90,298 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (threadIdx.x == 0) {
     tc::prefetch_tensormap(&tmA0);
     tc::prefetch_tensormap(&tmA1);
-    for (int s = 0; s < SA; ++s) { tc::mbar_init(a_full(s), 1); tc::mbar_init(a_empty(s), 1); }
-    for (int s = 0; s < NB; ++s) { tc::mbar_init(b_full(s), 1); tc::mbar_init(b_empty(s), 1); }
-    for (int s = 0; s < R; ++s) { tc::mbar_init(acc_full(s), 1); tc::mbar_init(acc_empty(s), 4); }
+    for (uint32_t s = 0; s < SA; ++s) { tc::mbar_init(a_full + 8 * s, 1); tc::mbar_init(a_empty + 8 * s, 1); }
+    for (uint32_t s = 0; s < NB; ++s) { tc::mbar_init(b_full + 8 * s, 1); tc::mbar_init(b_empty + 8 * s, 1); }
+    for (uint32_t s = 0; s < R; ++s) { tc::mbar_init(acc_full + 8 * s, 1); tc::mbar_init(acc_empty + 8 * s, 4); }
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_ptr_smem), 512);
-  for (int i = threadIdx.x; i < 2 * CB; i += TC_THREADS) s_stat[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * (int)CB; i += TC_THREADS) s_stat[i] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
+  const bool prof_on = (p.dbg & 8) != 0;
+  long long w0_ = 0, w1_ = 0;
+  const long long tstart_ = clock64();
 
   if (warp == 0) {
     // ---------------- activation producer: one TMA box per (input plane, channel chunk) -----------
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int zi = z_lo - 1; zi <= z_end; ++zi) {
-        if (zi < 0 || zi >= p.D) continue;
-        for (int kc = 0; kc < p.nkc; ++kc, ++it) {
-          const int s = it % SA;
-          tc::mbar_wait(a_empty(s), ((it / SA) & 1) ^ 1, 1);
-          tc::mbar_arrive_expect_tx(a_full(s), p.a_stage_bytes);
+    const bool leader = tc::elect_one();
+    RingPos a;
+    for (int zi = z_lo - 1; zi <= z_end; ++zi) {
+      if (zi < 0 || zi >= p.D) continue;
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * a.idx, a.phase ^ 1, 1));
+        if (leader && (p.dbg & 1)) tc::mbar_arrive(a_full + 8 * a.idx);
+        if (leader && !(p.dbg & 1)) {
+          tc::mbar_arrive_expect_tx(a_full + 8 * a.idx, p.a_stage_bytes);
           const bool first = kc < p.nkc0;
-          const int c8 = first ? n * (p.C0 >> 3) + kc * (p.KC >> 3) : n * (p.C1 >> 3) + (kc - p.nkc0) * (p.KC >> 3);
-          tc::tma_load_4d(smem_base + s * p.a_stage_bytes, first ? &tmA0 : &tmA1, a_full(s), (w0 - 1) * 8, h0 - 1, zi, c8);
+          const int c8 = first ? n * (p.C0 >> 3) + kc * (2 * KSTEPS) : n * (p.C1 >> 3) + (kc - p.nkc0) * (2 * KSTEPS);
+          tc::tma_load_4d(smem_base + a.idx * p.a_stage_bytes, first ? &tmA0 : &tmA1, a_full + 8 * a.idx, (w0 - 1) * 8, h0 - 1, zi, c8);
         }
+        a.advance(SA);
       }
     }
   } else if (warp == 6) {
     // ---------------- weight producer: ready-made operand tiles, bulk copies ----------------------
-    if (lane == 0) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)cb * (9 * p.nkc) * p.b_tile_bytes;
-      if (p.resident) {
+    const bool leader = tc::elect_one();
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)cb * (9 * p.nkc) * p.b_tile_bytes;
+    if (p.resident) {
+      if (leader)
         for (int t = 0; t < 9 * p.nkc; ++t) {
-          tc::mbar_arrive_expect_tx(b_full(t), p.b_tile_bytes);
-          tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full(t));
+          tc::mbar_arrive_expect_tx(b_full + 8 * t, p.b_tile_bytes);
+          tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
         }
-      } else {
-        uint32_t it = 0;
-        for (int zi = z_lo - 1; zi <= z_end; ++zi) {
-          if (zi < 0 || zi >= p.D) continue;
-          for (int t = 0; t < 9 * p.nkc; ++t, ++it) {
-            const int s = it % NB;
-            tc::mbar_wait(b_empty(s), ((it / NB) & 1) ^ 1, 2);
-            tc::mbar_arrive_expect_tx(b_full(s), p.b_tile_bytes);
-            tc::bulk_load(smem_base + p.off_b + s * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full(s));
+    } else {
+      RingPos b;
+      for (int zi = z_lo - 1; zi <= z_end; ++zi) {
+        if (zi < 0 || zi >= p.D) continue;
+        for (int t = 0; t < 9 * p.nkc; ++t) {
+          DWMH_TIMED_WAIT(w0_, tc::mbar_wait(b_empty + 8 * b.idx, b.phase ^ 1, 2));
+          if (leader) {
+            tc::mbar_arrive_expect_tx(b_full + 8 * b.idx, p.b_tile_bytes);
+            tc::bulk_load(smem_base + p.off_b + b.idx * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * b.idx);
           }
+          b.advance(NB);
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer ------------------------------------------------------------------
-    if (lane == 0) {
-      const uint32_t idesc0 = tc::instr_desc_f16(p.fmt, 128, 0);
-      const uint32_t b_lbo = 3u * CB * 16u;
-      const int last_zi = min(z_end, p.D - 1);
-      uint32_t a_it = 0, b_it = 0;
-      int next_fresh = z_lo, next_done = z_lo;
-      for (int zi = z_lo - 1; zi <= z_end; ++zi) {
-        if (zi < 0 || zi >= p.D) continue;
-        const int zo_lo = max(zi - 1, z_lo), zo_hi = min(zi + 1, z_end - 1);
-        while (next_fresh <= zo_hi) {          // slot must have been zeroed by the epilogue
-          const int u = next_fresh - z_lo;
-          tc::mbar_wait(acc_empty(u % R), (u / R) & 1, 3);
-          ++next_fresh;
-        }
-        tc::tc_fence_after();
-        int nseg = 0, prev_slot = -2;
-        uint32_t seg_col[3], seg_n[3], seg_j[3];
-        for (int zo = zo_lo; zo <= zo_hi; ++zo) {
-          const int slot = (zo - z_lo) % R;
-          if (nseg > 0 && slot == prev_slot + 1 && seg_n[nseg - 1] + CB <= 256) seg_n[nseg - 1] += CB;
-          else { seg_col[nseg] = slot * CB; seg_n[nseg] = CB; seg_j[nseg] = zo - zi + 1; ++nseg; }
-          prev_slot = slot;
-        }
-        for (int kc = 0; kc < p.nkc; ++kc, ++a_it) {
-          const int sa = a_it % SA;
-          tc::mbar_wait(a_full(sa), (a_it / SA) & 1, 4);
+    // ---------------- MMA issuer: warp-uniform control flow, one elected lane issues ---------------
+    // A single warp has to sustain one tcgen05.mma per ~50 cycles on the narrow layers, so the code
+    // between two MMAs is kept to a descriptor add: ring cursors instead of div/mod, and a straight-line
+    // unrolled burst of 9 taps x KSTEPS per channel chunk when the weights are resident.
+    const bool elected = tc::elect_one();
+    const bool leader = elected && !(p.dbg & 2);
+    const uint32_t idesc0 = tc::instr_desc_f16(p.fmt, 128, 0);
+    const uint32_t idesc1 = idesc0 | ((CB >> 3) << 17);
+    const uint32_t b_lbo16 = 3u * CB;                                  // LBO of the weight tiles, in 16-B units
+    const uint32_t kstep_b = 2u * b_lbo16, tile16 = p.b_tile_bytes >> 4;
+    const uint32_t a_hi = (uint32_t)((TC_PW * 16) >> 4) | (1u << 14);  // SBO = 160 B, descriptor version 1
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);                    // SBO = 128 B
+    const uint32_t a_lbo_field = (uint32_t)(TC_PLANE_BYTES >> 4) << 16;
+    const uint32_t b_lo_res = ((smem_base + p.off_b) >> 4) | (b_lbo16 << 16);
+    const int last_zi = min(z_end, p.D - 1);
+    if (p.resident)
+      for (int t = 0; t < 9 * p.nkc; ++t) tc::mbar_wait(b_full + 8 * t, 0, 5);
+    RingPos a, b, fresh, done;
+    uint32_t lo_slot = 0;
+    int next_fresh = z_lo, next_done = z_lo, zo_lo_prev = z_lo;
+    for (int zi = z_lo - 1; zi <= z_end; ++zi) {
+      if (zi < 0 || zi >= p.D) continue;
+      const int zo_lo = max(zi - 1, z_lo), zo_hi = min(zi + 1, z_end - 1);
+      if (zo_lo != zo_lo_prev) { lo_slot = (lo_slot + 1 == R) ? 0 : lo_slot + 1; zo_lo_prev = zo_lo; }
+      const int fresh_from = next_fresh;        // output planes >= fresh_from are first touched by this input plane
+      while (next_fresh <= zo_hi) {             // the epilogue must have drained the slot's previous use
+        DWMH_TIMED_WAIT(w1_, tc::mbar_wait(acc_empty + 8 * fresh.idx, fresh.phase ^ 1, 3));
+        fresh.advance(R);
+        ++next_fresh;
+      }
+      const uint32_t cnt = (uint32_t)(zo_hi - zo_lo + 1), j_lo = (uint32_t)(zo_lo - zi + 1);
+      if (p.resident && cnt == 3 && lo_slot + 3 <= R && 3 * CB <= 256 && fresh_from == zo_hi) {
+        // ---- steady state (interior plane, slots contiguous, exactly output plane zi+1 is new) ----
+        const uint32_t col = tmem + lo_slot * CB;
+        const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17), id3 = idesc0 | (((3 * CB) >> 3) << 17);
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
           tc::tc_fence_after();
-          const uint32_t a_base = smem_base + sa * p.a_stage_bytes;
-          for (int sft = 0; sft < 9; ++sft) {
-            int sb;
-            if (p.resident) { sb = kc * 9 + sft; tc::mbar_wait(b_full(sb), 0, 5); }
-            else { sb = b_it % NB; tc::mbar_wait(b_full(sb), (b_it / NB) & 1, 6); }
-            tc::tc_fence_after();
-            const uint32_t b_base = smem_base + p.off_b + sb * p.b_tile_bytes;
-            const uint32_t a_tap = a_base + (sft / 3) * (TC_PW * 16) + (sft % 3) * 16;
-            for (int kk = 0; kk < (p.KC >> 4); ++kk) {
-              const uint64_t adesc = tc::smem_desc_kmajor_noswizzle(a_tap + kk * 2 * TC_PLANE_BYTES, TC_PLANE_BYTES, TC_PW * 16);
-              for (int g = 0; g < nseg; ++g) {
-                const uint64_t bdesc = tc::smem_desc_kmajor_noswizzle(b_base + kk * 2 * b_lbo + seg_j[g] * CB * 16, b_lbo, 128);
-                tc::umma_f16(tmem + seg_col[g], adesc, bdesc, idesc0 | ((seg_n[g] >> 3) << 17), 1u);
+          if (leader) {
+            const uint32_t a_lo0 = ((smem_base + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
+#pragma unroll
+            for (int sft = 0; sft < 9; ++sft) {
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                const uint64_t adesc = tc_desc(a_hi, a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4));
+                if (sft == 0 && kk == 0) {
+                  if (kc == 0) {     // first MMA of the plane: planes zi-1, zi accumulate, plane zi+1 is overwritten
+                    tc::umma_f16(col, adesc, tc_desc(b_hi, bl), id2, 1u);
+                    tc::umma_f16(col + 2 * CB, adesc, tc_desc(b_hi, bl + 2 * CB), idesc1, 0u);
+                  } else tc::umma_f16(col, adesc, tc_desc(b_hi, bl), id3, 1u);
+                } else tc::umma_f16(col, adesc, tc_desc(b_hi, bl + kk * kstep_b), id3, 1u);
+              }
+              bl += tile16;
+            }
+          }
+          if (elected) tc::umma_commit(a_empty + 8 * a.idx);
+          a.advance(SA);
+        }
+        if (elected) tc::umma_commit(acc_full + 8 * done.idx);        // output plane zi-1 is complete
+        done.advance(R);
+        ++next_done;
+        __syncwarp();
+        continue;
+      }
+      const uint32_t run0 = min(cnt, R - lo_slot);                     // slots before the ring wraps
+      const bool single = run0 == cnt && cnt * CB <= 256;
+      // general segment list (ring wrap and/or N > 256), kept in scalars (no local-memory arrays)
+      uint32_t nseg = 0, sc0 = 0, sc1 = 0, sc2 = 0, sb0 = 0, sb1 = 0, sb2 = 0, si0 = 0, si1 = 0, si2 = 0;
+      if (!single) {
+        uint32_t i = 0;
+        while (i < cnt) {
+          const uint32_t slot = lo_slot + i < R ? lo_slot + i : lo_slot + i - R;
+          uint32_t len = min(cnt - i, R - slot);
+          len = min(len, 256u / CB);
+          const uint32_t c_ = tmem + slot * CB, b_ = (j_lo + i) * CB, d_ = idesc0 | (((len * CB) >> 3) << 17);
+          if (nseg == 0) { sc0 = c_; sb0 = b_; si0 = d_; } else if (nseg == 1) { sc1 = c_; sb1 = b_; si1 = d_; } else { sc2 = c_; sb2 = b_; si2 = d_; }
+          ++nseg; i += len;
+        }
+      }
+      const uint32_t col0 = tmem + lo_slot * CB, boff0 = j_lo * CB, idesc_s = idesc0 | (((cnt * CB) >> 3) << 17);
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
+        tc::tc_fence_after();
+        const uint32_t a_lo0 = ((smem_base + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+        if (p.resident) {
+          const uint32_t b_lo_kc = b_lo_res + (uint32_t)kc * 9u * tile16;
+          if (kc == 0) {
+            // first MMA of the plane: slot by slot, overwriting (accumulate = 0) first-touched slots
+            for (uint32_t i = 0; i < cnt; ++i) {
+              const uint32_t slot = lo_slot + i < R ? lo_slot + i : lo_slot + i - R;
+              if (leader) tc::umma_f16(tmem + slot * CB, tc_desc(a_hi, a_lo0), tc_desc(b_hi, b_lo_kc + (j_lo + i) * CB), idesc1,
+                                       (zo_lo + (int)i) >= fresh_from ? 0u : 1u);
+            }
+          }
+          if (single) {
+            if (leader) {
+              uint32_t bl = b_lo_kc + boff0;
+#pragma unroll
+              for (int sft = 0; sft < 9; ++sft) {
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  const uint32_t al = a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4);
+                  if (sft == 0 && kk == 0) { if (kc != 0) tc::umma_f16(col0, tc_desc(a_hi, al), tc_desc(b_hi, bl), idesc_s, 1u); }
+                  else tc::umma_f16(col0, tc_desc(a_hi, al), tc_desc(b_hi, bl + kk * kstep_b), idesc_s, 1u);
+                }
+                bl += tile16;
               }
             }
-            if (!p.resident) { tc::umma_commit(b_empty(sb)); ++b_it; }
+          } else if (leader) {
+            for (int sft = 0; sft < 9; ++sft)
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                if (kc == 0 && sft == 0 && kk == 0) continue;
+                const uint64_t adesc = tc_desc(a_hi, a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4));
+                const uint32_t bl = b_lo_kc + sft * tile16 + kk * kstep_b;
+                tc::umma_f16(sc0, adesc, tc_desc(b_hi, bl + sb0), si0, 1u);
+                if (nseg > 1) tc::umma_f16(sc1, adesc, tc_desc(b_hi, bl + sb1), si1, 1u);
+                if (nseg > 2) tc::umma_f16(sc2, adesc, tc_desc(b_hi, bl + sb2), si2, 1u);
+              }
           }
-          tc::umma_commit(a_empty(sa));
+        } else {
+#pragma unroll
+          for (int sft = 0; sft < 9; ++sft) {
+            DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
+            tc::tc_fence_after();
+            const uint32_t b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+            const uint32_t a_lo1 = a_lo0 + (sft / 3) * TC_PW + (sft % 3);
+            if (sft == 0 && kc == 0) {
+              for (uint32_t i = 0; i < cnt; ++i) {
+                const uint32_t slot = lo_slot + i < R ? lo_slot + i : lo_slot + i - R;
+                if (leader) tc::umma_f16(tmem + slot * CB, tc_desc(a_hi, a_lo1), tc_desc(b_hi, b_lo0 + (j_lo + i) * CB), idesc1,
+                                         (zo_lo + (int)i) >= fresh_from ? 0u : 1u);
+              }
+            }
+            if (leader) {
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                if (sft == 0 && kk == 0 && kc == 0) continue;
+                const uint64_t adesc = tc_desc(a_hi, a_lo1 + kk * (2 * TC_PLANE_BYTES >> 4));
+                const uint32_t bl = b_lo0 + kk * kstep_b;
+                if (single) tc::umma_f16(col0, adesc, tc_desc(b_hi, bl + boff0), idesc_s, 1u);
+                else {
+                  tc::umma_f16(sc0, adesc, tc_desc(b_hi, bl + sb0), si0, 1u);
+                  if (nseg > 1) tc::umma_f16(sc1, adesc, tc_desc(b_hi, bl + sb1), si1, 1u);
+                  if (nseg > 2) tc::umma_f16(sc2, adesc, tc_desc(b_hi, bl + sb2), si2, 1u);
+                }
+              }
+            }
+            if (elected) tc::umma_commit(b_empty + 8 * b.idx);
+            b.advance(NB);
+          }
         }
-        const int done_upto = (zi == last_zi) ? z_end - 1 : zi - 1;
-        while (next_done <= done_upto) { tc::umma_commit(acc_full((next_done - z_lo) % R)); ++next_done; }
+        if (elected) tc::umma_commit(a_empty + 8 * a.idx);
+        a.advance(SA);
       }
+      const int done_upto = (zi == last_zi) ? z_end - 1 : zi - 1;
+      while (next_done <= done_upto) {
+        if (elected) tc::umma_commit(acc_full + 8 * done.idx);
+        done.advance(R);
+        ++next_done;
+      }
+      __syncwarp();
     }
   } else {
     // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ---------------------------
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int h = h0 + (row >> 3), w = w0 + (row & 7);
-    const bool valid = h < p.H && w < p.W;
+    const bool valid = h < p.H && w < p.W && !(p.dbg & 4);
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
     const int nch = CB >> 4;
-    for (int c = 0; c < R * CB; c += 16) tc::tmem_st16_zero(tm_lane + c);
-    tc::tmem_st_wait();
-    tc::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) for (int s = 0; s < R; ++s) tc::mbar_arrive(acc_empty(s));
-    float rs[8], rq[8];
+    constexpr int NACC = SMALL_CB ? 32 : 8;
+    float rs[NACC], rq[NACC];      // SMALL_CB: per-thread per-channel running sums; else per-lane column totals
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+    for (int i = 0; i < NACC; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
     const size_t V = (size_t)p.D * p.H * p.W;
     uint4* out_base = reinterpret_cast<uint4*>(p.out) + ((size_t)n * (p.Cout >> 3) + (size_t)cb * (CB >> 3)) * V;
+    uint32_t slot = 0, phase = 0;
     for (int zo = z_lo; zo < z_end; ++zo) {
-      const int u = zo - z_lo, slot = u % R;
-      tc::mbar_wait(acc_full(slot), (u / R) & 1, 7);
+      DWMH_TIMED_WAIT(w0_, tc::mbar_wait(acc_full + 8 * slot, phase, 7));
       tc::tc_fence_after();
       uint4* outp = out_base + ((size_t)zo * p.H + h) * p.W + w;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < (SMALL_CB ? 2 : 8); ++ch) {
         if (ch < nch) {
           uint32_t r[16];
           tc::tmem_ld16(tm_lane + slot * CB + ch * 16, r);
           tc::tmem_ld_wait();
-          float a[16], b[16];
+          float a[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { a[i] = valid ? __uint_as_float(r[i]) : 0.f; b[i] = a[i] * a[i]; }
+          for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(r[i]);
           if (valid) {
             outp[(size_t)(2 * ch) * V] = pack8<T>(a);
             outp[(size_t)(2 * ch + 1) * V] = pack8<T>(a + 8);
           }
-          // transposing butterfly: afterwards lane l holds the 32-row total of column (l & 15)
+          if constexpr (SMALL_CB) {
+            if (valid) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { rs[ch * 16 + i] += a[i]; rq[ch * 16 + i] = fmaf(a[i], a[i], rq[ch * 16 + i]); }
+            }
+          } else {
+            float b[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { a[i] = valid ? a[i] : 0.f; b[i] = a[i] * a[i]; }
+            // transposing butterfly: afterwards lane l holds the 32-row total of column (l & 15)
+#pragma unroll
+            for (int k = 8; k >= 1; k >>= 1) {
+              const bool up = (lane & k) != 0;
+#pragma unroll
+              for (int i = 0; i < k; ++i) {
+                const float sa_ = up ? a[i] : a[i + k], ka_ = up ? a[i + k] : a[i];
+                const float sb_ = up ? b[i] : b[i + k], kb_ = up ? b[i + k] : b[i];
+                a[i] = ka_ + __shfl_xor_sync(0xffffffffu, sa_, k);
+                b[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, k);
+              }
+            }
+            rs[ch] += a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16);
+            rq[ch] += b[0] + __shfl_xor_sync(0xffffffffu, b[0], 16);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(acc_empty + 8 * slot);
+      if (++slot == R) { slot = 0; phase ^= 1; }
+    }
+    if constexpr (SMALL_CB) {
+      // one transposing reduction for the whole CTA lifetime
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        if (ch < nch) {
+          float a[16], b[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { a[i] = rs[ch * 16 + i]; b[i] = rq[ch * 16 + i]; }
 #pragma unroll
           for (int k = 8; k >= 1; k >>= 1) {
             const bool up = (lane & k) != 0;
@@ -230,28 +393,26 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               b[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, k);
             }
           }
-          rs[ch] += a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16);
-          rq[ch] += b[0] + __shfl_xor_sync(0xffffffffu, b[0], 16);
+          const float ts = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16), tq = b[0] + __shfl_xor_sync(0xffffffffu, b[0], 16);
+          if (lane < 16) { atomicAdd(&s_stat[ch * 16 + lane], ts); atomicAdd(&s_stat[CB + ch * 16 + lane], tq); }
         }
       }
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch)
-        if (ch < nch) tc::tmem_st16_zero(tm_lane + slot * CB + ch * 16);
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(acc_empty(slot));
-    }
-    if (lane < 16) {
+    } else if (lane < 16) {
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
         if (ch < nch) { atomicAdd(&s_stat[ch * 16 + lane], rs[ch]); atomicAdd(&s_stat[CB + ch * 16 + lane], rq[ch]); }
     }
   }
+  if (prof_on && lane == 0 && (warp <= 2 || warp == 6)) {
+    const int role = warp == 6 ? 3 : warp;          // 0 act producer, 1 mma, 2 epilogue (warp 2), 3 weight producer
+    atomicAdd(p.prof + role * 4 + 0, (unsigned long long)w0_);
+    atomicAdd(p.prof + role * 4 + 1, (unsigned long long)w1_);
+    atomicAdd(p.prof + role * 4 + 2, (unsigned long long)(clock64() - tstart_));
+  }
   tc::tc_fence_before();
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * CB; i += TC_THREADS) {
-    const int c = i % CB, which = i / CB;
+  for (int i = threadIdx.x; i < 2 * (int)CB; i += TC_THREADS) {
+    const int c = i % (int)CB, which = i / (int)CB;
     atomicAdd(p.sums + ((size_t)n * p.Cout + (size_t)cb * CB + c) * 2 + which, (double)s_stat[i]);
   }
   if (warp == 1) tc::tmem_dealloc(tmem, 512);
@@ -393,11 +554,17 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   return 0;
 }
 
-inline int tc_init_attributes(bool bf16) {
-  cudaError_t e = bf16 ? cudaFuncSetAttribute(conv3_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)
-                       : cudaFuncSetAttribute(conv3_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+template <typename T>
+inline int tc_set_attr_all() {
+  cudaError_t e = cudaSuccess;
+#define DWMH_TC_ATTR(K, S) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)
+  DWMH_TC_ATTR(1, true); DWMH_TC_ATTR(2, true); DWMH_TC_ATTR(4, true);
+  DWMH_TC_ATTR(1, false); DWMH_TC_ATTR(2, false); DWMH_TC_ATTR(4, false);
+#undef DWMH_TC_ATTR
   return e == cudaSuccess ? 0 : 1;
 }
+
+inline int tc_init_attributes(bool bf16) { return bf16 ? tc_set_attr_all<__nv_bfloat16>() : tc_set_attr_all<__half>(); }
 
 template <typename T>
 int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, std::string* err) {
@@ -407,10 +574,30 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   int ZB = kp.D;
   while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 8) ZB = (ZB + 1) / 2;
   kp.ZB = ZB; kp.nzb = (kp.D + ZB - 1) / ZB;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DWMH_TC_DEBUG"); dbg = e ? atoi(e) : 0; } kp.dbg = dbg; }
   const unsigned grid = (unsigned)((long long)nb * kp.ncb * kp.nzb * tiles);
-  conv3_tc_kernel<T><<<grid, TC_THREADS, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
+  static unsigned long long* prof_dev = nullptr;
+  if (kp.dbg & 8) {
+    if (!prof_dev) cudaMalloc((void**)&prof_dev, 16 * sizeof(unsigned long long));
+    cudaMemsetAsync(prof_dev, 0, 16 * sizeof(unsigned long long), st);
+  }
+  kp.prof = prof_dev;
+  const int ks = kp.KC / 16;
+  const bool small = kp.CB <= 32;
+#define DWMH_TC_LAUNCH(K, S) conv3_tc_kernel<T, K, S><<<grid, TC_THREADS, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
+  if (small) { if (ks == 1) DWMH_TC_LAUNCH(1, true); else if (ks == 2) DWMH_TC_LAUNCH(2, true); else DWMH_TC_LAUNCH(4, true); }
+  else { if (ks == 1) DWMH_TC_LAUNCH(1, false); else if (ks == 2) DWMH_TC_LAUNCH(2, false); else DWMH_TC_LAUNCH(4, false); }
+#undef DWMH_TC_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv3_tc_kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+  if (kp.dbg & 8) {
+    unsigned long long h[16];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost);
+    const double g = (double)grid;
+    fprintf(stderr, "tcprof C0=%d C1=%d Cout=%d CB=%d KC=%d D=%d res=%d grid=%u planes/cta=%d | act-prod wait_empty %.0f tot %.0f | mma wait_a %.0f wait_acc/b %.0f tot %.0f | epi wait_full %.0f tot %.0f | w-prod wait %.0f tot %.0f (cycles per CTA)\n",
+            kp.C0, kp.C1, kp.Cout, kp.CB, kp.KC, kp.D, kp.resident, grid, kp.ZB, h[0] / g, h[2] / g, h[4] / g, h[5] / g, h[6] / g, h[8] / g, h[10] / g, h[12] / g, h[14] / g);
+  }
   return 0;
 }
 

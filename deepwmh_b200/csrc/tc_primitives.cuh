@@ -35,6 +35,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     if (++spins > (1u << 26)) { printf("dwmh tc: mbarrier timeout tag=%d block=%d thread=%d\n", tag, blockIdx.x, threadIdx.x); __trap(); }
   }
 }
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- TMA --------------------------------------------------------------------------------------
