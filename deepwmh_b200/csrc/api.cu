@@ -56,6 +56,8 @@ struct Layer {
   bool have_w = false, have_g = false, have_b = false;
   // device
   void* out = nullptr;              // [maxN][cout/8][V][8] T
+  void* s2d = nullptr;              // parity-split copy for a strided tcgen05 consumer
+  int s2d_s[3] = {1, 1, 1};
   float* w_dev = nullptr;           // generic packing
   float* gamma_dev = nullptr; float* beta_dev = nullptr;
   double* sums = nullptr;           // into the stats arena
@@ -194,7 +196,7 @@ extern "C" int dwmh_destroy(dwmh_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (auto& L : c->layers) { free_dev(L.out); free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc); }
+  for (auto& L : c->layers) { free_dev(L.out); free_dev(L.s2d); free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc); }
   free_dev(c->w_head_dev); free_dev(c->stats_arena); free_dev(c->probs); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
   free_dev(c->hv_vol); free_dev(c->hv_pad); free_dev(c->hv_agg); free_dev(c->hv_wgt); free_dev(c->hv_seg);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -319,6 +321,13 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     if (L.kind != L_CONV) continue;
     const void* in0 = c->layers[L.in0].out;
     const void* in1 = L.in1 >= 0 ? c->layers[L.in1].out : nullptr;
+    const bool strided = L.s[0] != 1 || L.s[1] != 1 || L.s[2] != 1;
+    if (strided && L.k[0] == 3 && L.k[1] == 3 && L.k[2] == 3 && L.c0 % 16 == 0 && L.c1 == 0 && L.cout % 16 == 0) {
+      Layer& P = c->layers[L.in0];
+      if (!P.s2d) CU_TRY(cudaMalloc(&P.s2d, (size_t)maxN * P.cout * P.vout() * c->elt));
+      for (int a_ = 0; a_ < 3; ++a_) P.s2d_s[a_] = L.s[a_];
+      in0 = P.s2d;
+    }
     std::string why;
     if (tc_prepare(L.tc, L.w, L.c0, L.c1, L.cout, L.k, L.s, L.in_sp, L.out_sp, maxN, c->bf16, in0, in1, L.out, &why)) {
       if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
@@ -490,7 +499,8 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
       const int64_t V = L.vout();
       const int gx = (int)std::min<int64_t>((V + 255) / 256, 1024);
       dim3 grid(gx, nb * (L.cout >> 3));
-      instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.out, np, L.cout, V);
+      S2dParams sp{L.s2d, L.out_sp[0], L.out_sp[1], L.out_sp[2], L.s2d_s[0], L.s2d_s[1], L.s2d_s[2]};
+      instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.out, np, L.cout, V, sp);
       c->launches++;
     }
   }

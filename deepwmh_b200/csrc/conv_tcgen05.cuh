@@ -38,13 +38,21 @@ constexpr int TC_THREADS = 224;
 constexpr int TC_TH = 16, TC_TW = 8;
 constexpr int TC_PH = 18, TC_PW = 10;
 constexpr int TC_PLANE_BYTES = TC_PH * TC_PW * 16;     // one 8-channel chunk of a haloed plane
-constexpr int TC_MAX_SA = 4, TC_MAX_NB = 20, TC_MAX_R = 16;
+constexpr int TC_MAX_SA = 4, TC_MAX_NB = 40, TC_MAX_R = 16;
 constexpr int TC_SMEM_MAX = 232448;                    // 227 KB opt-in limit
-constexpr int TC_SMEM_RESERVED = 2048;                 // barriers + TMEM pointer + statistics
+constexpr int TC_SMEM_RESERVED = 3072;                 // barriers + TMEM pointer + statistics
+
+// One parity class of a strided conv (a plain stride-1 conv has exactly one class).  The producer tensor of
+// a strided conv is stored a second time parity-split ("space to depth": [n][class][C/8][D/sd][H/sh][W/sw][8]),
+// so a strided tap is again a dense TMA box plus a start-address shift.  tapmask: bit (dy*3+dx) = in-plane
+// shifts this class uses; the sub-plane t of this class feeds output planes t+jlo .. t+jlo+jcnt-1.
+struct TcClassDesc { int tapmask, jlo, jcnt, tile0; };
 
 struct TcKParams {
   const void* wpack; void* out; double* sums;
   int C0, C1, Cout, CB, KC, nkc, nkc0;
+  int nclass, Jlo, Jhi, jmax, tiles_per_kc, Din;
+  TcClassDesc cls[8];
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
   int SA, NB, resident, R, fmt;
   unsigned long long* prof;   // dbg & 8: per-role wait/total cycle counters
@@ -109,41 +117,51 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // ---------------- activation producer: one TMA box per (input plane, channel chunk) -----------
     const bool leader = tc::elect_one();
     RingPos a;
-    for (int zi = z_lo - 1; zi <= z_end; ++zi) {
-      if (zi < 0 || zi >= p.D) continue;
-      for (int kc = 0; kc < p.nkc; ++kc) {
-        DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * a.idx, a.phase ^ 1, 1));
-        if (leader && (p.dbg & 1)) tc::mbar_arrive(a_full + 8 * a.idx);
-        if (leader && !(p.dbg & 1)) {
-          tc::mbar_arrive_expect_tx(a_full + 8 * a.idx, p.a_stage_bytes);
-          const bool first = kc < p.nkc0;
-          const int c8 = first ? n * (p.C0 >> 3) + kc * (2 * KSTEPS) : n * (p.C1 >> 3) + (kc - p.nkc0) * (2 * KSTEPS);
-          tc::tma_load_4d(smem_base + a.idx * p.a_stage_bytes, first ? &tmA0 : &tmA1, a_full + 8 * a.idx, (w0 - 1) * 8, h0 - 1, zi, c8);
+    for (int t = z_lo - p.Jhi; t <= z_end - 1 - p.Jlo; ++t) {
+      if (t < 0 || t >= p.Din) continue;
+      for (int c = 0; c < p.nclass; ++c) {
+        if (max(t + p.cls[c].jlo, z_lo) > min(t + p.cls[c].jlo + p.cls[c].jcnt - 1, z_end - 1)) continue;
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * a.idx, a.phase ^ 1, 1));
+          if (leader && (p.dbg & 1)) tc::mbar_arrive(a_full + 8 * a.idx);
+          if (leader && !(p.dbg & 1)) {
+            tc::mbar_arrive_expect_tx(a_full + 8 * a.idx, p.a_stage_bytes);
+            const bool first = kc < p.nkc0;
+            const int c8 = first ? (n * p.nclass + c) * (p.C0 >> 3) + kc * (2 * KSTEPS) : n * (p.C1 >> 3) + (kc - p.nkc0) * (2 * KSTEPS);
+            tc::tma_load_4d(smem_base + a.idx * p.a_stage_bytes, first ? &tmA0 : &tmA1, a_full + 8 * a.idx, (w0 - 1) * 8, h0 - 1, t, c8);
+          }
+          a.advance(SA);
         }
-        a.advance(SA);
       }
     }
   } else if (warp == 6) {
     // ---------------- weight producer: ready-made operand tiles, bulk copies ----------------------
     const bool leader = tc::elect_one();
-    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)cb * (9 * p.nkc) * p.b_tile_bytes;
+    const int ntile = p.nkc * p.tiles_per_kc;
+    const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)cb * ntile * p.b_tile_bytes;
     if (p.resident) {
       if (leader)
-        for (int t = 0; t < 9 * p.nkc; ++t) {
+        for (int t = 0; t < ntile; ++t) {
           tc::mbar_arrive_expect_tx(b_full + 8 * t, p.b_tile_bytes);
           tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
         }
     } else {
       RingPos b;
-      for (int zi = z_lo - 1; zi <= z_end; ++zi) {
-        if (zi < 0 || zi >= p.D) continue;
-        for (int t = 0; t < 9 * p.nkc; ++t) {
-          DWMH_TIMED_WAIT(w0_, tc::mbar_wait(b_empty + 8 * b.idx, b.phase ^ 1, 2));
-          if (leader) {
-            tc::mbar_arrive_expect_tx(b_full + 8 * b.idx, p.b_tile_bytes);
-            tc::bulk_load(smem_base + p.off_b + b.idx * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * b.idx);
-          }
-          b.advance(NB);
+      for (int t = z_lo - p.Jhi; t <= z_end - 1 - p.Jlo; ++t) {
+        if (t < 0 || t >= p.Din) continue;
+        for (int c = 0; c < p.nclass; ++c) {
+          if (max(t + p.cls[c].jlo, z_lo) > min(t + p.cls[c].jlo + p.cls[c].jcnt - 1, z_end - 1)) continue;
+          const int ntaps = __popc(p.cls[c].tapmask);
+          for (int kc = 0; kc < p.nkc; ++kc)
+            for (int ti = 0; ti < ntaps; ++ti) {
+              const int tile = kc * p.tiles_per_kc + p.cls[c].tile0 + ti;
+              DWMH_TIMED_WAIT(w0_, tc::mbar_wait(b_empty + 8 * b.idx, b.phase ^ 1, 2));
+              if (leader) {
+                tc::mbar_arrive_expect_tx(b_full + 8 * b.idx, p.b_tile_bytes);
+                tc::bulk_load(smem_base + p.off_b + b.idx * p.b_tile_bytes, wsrc + (size_t)tile * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * b.idx);
+              }
+              b.advance(NB);
+            }
         }
       }
     }
@@ -151,36 +169,37 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // ---------------- MMA issuer: warp-uniform control flow, one elected lane issues ---------------
     // A single warp has to sustain one tcgen05.mma per ~50 cycles on the narrow layers, so the code
     // between two MMAs is kept to a descriptor add: ring cursors instead of div/mod, and a straight-line
-    // unrolled burst of 9 taps x KSTEPS per channel chunk when the weights are resident.
+    // unrolled burst of 9 taps x KSTEPS per channel chunk in the steady state of a stride-1 layer.
     const bool elected = tc::elect_one();
     const bool leader = elected && !(p.dbg & 2);
     const uint32_t idesc0 = tc::instr_desc_f16(p.fmt, 128, 0);
     const uint32_t idesc1 = idesc0 | ((CB >> 3) << 17);
-    const uint32_t b_lbo16 = 3u * CB;                                  // LBO of the weight tiles, in 16-B units
+    const uint32_t b_lbo16 = (uint32_t)p.jmax * CB;                    // LBO of the weight tiles, in 16-B units
     const uint32_t kstep_b = 2u * b_lbo16, tile16 = p.b_tile_bytes >> 4;
     const uint32_t a_hi = (uint32_t)((TC_PW * 16) >> 4) | (1u << 14);  // SBO = 160 B, descriptor version 1
     const uint32_t b_hi = (128u >> 4) | (1u << 14);                    // SBO = 128 B
     const uint32_t a_lbo_field = (uint32_t)(TC_PLANE_BYTES >> 4) << 16;
     const uint32_t b_lo_res = ((smem_base + p.off_b) >> 4) | (b_lbo16 << 16);
-    const int last_zi = min(z_end, p.D - 1);
+    const int t_first = z_lo - p.Jhi, t_last_nominal = z_end - 1 - p.Jlo;
+    const int last_t = min(t_last_nominal, p.Din - 1);
+    const bool plain = p.nclass == 1 && p.Jlo == -1 && p.Jhi == 1;     // stride-1 3x3x3
     if (p.resident)
-      for (int t = 0; t < 9 * p.nkc; ++t) tc::mbar_wait(b_full + 8 * t, 0, 5);
+      for (int t = 0; t < p.nkc * p.tiles_per_kc; ++t) tc::mbar_wait(b_full + 8 * t, 0, 5);
     RingPos a, b, fresh, done;
     uint32_t lo_slot = 0;
     int next_fresh = z_lo, next_done = z_lo, zo_lo_prev = z_lo;
-    for (int zi = z_lo - 1; zi <= z_end; ++zi) {
-      if (zi < 0 || zi >= p.D) continue;
-      const int zo_lo = max(zi - 1, z_lo), zo_hi = min(zi + 1, z_end - 1);
+    for (int t = t_first; t <= t_last_nominal; ++t) {
+      if (t < 0 || t >= p.Din) continue;
+      const int zo_lo = max(t + p.Jlo, z_lo), zo_hi = min(t + p.Jhi, z_end - 1);
       if (zo_lo != zo_lo_prev) { lo_slot = (lo_slot + 1 == R) ? 0 : lo_slot + 1; zo_lo_prev = zo_lo; }
-      const int fresh_from = next_fresh;        // output planes >= fresh_from are first touched by this input plane
+      const int fresh_from = next_fresh;        // output planes >= fresh_from are first touched in this step
       while (next_fresh <= zo_hi) {             // the epilogue must have drained the slot's previous use
         DWMH_TIMED_WAIT(w1_, tc::mbar_wait(acc_empty + 8 * fresh.idx, fresh.phase ^ 1, 3));
         fresh.advance(R);
         ++next_fresh;
       }
-      const uint32_t cnt = (uint32_t)(zo_hi - zo_lo + 1), j_lo = (uint32_t)(zo_lo - zi + 1);
-      if (p.resident && cnt == 3 && lo_slot + 3 <= R && 3 * CB <= 256 && fresh_from == zo_hi) {
-        // ---- steady state (interior plane, slots contiguous, exactly output plane zi+1 is new) ----
+      if (plain && p.resident && zo_hi - zo_lo == 2 && lo_slot + 3 <= R && 3 * CB <= 256 && fresh_from == zo_hi) {
+        // ---- steady state (interior plane, slots contiguous, exactly output plane t+1 is new) ----
         const uint32_t col = tmem + lo_slot * CB;
         const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17), id3 = idesc0 | (((3 * CB) >> 3) << 17);
         for (int kc = 0; kc < p.nkc; ++kc) {
@@ -195,7 +214,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               for (int kk = 0; kk < KSTEPS; ++kk) {
                 const uint64_t adesc = tc_desc(a_hi, a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4));
                 if (sft == 0 && kk == 0) {
-                  if (kc == 0) {     // first MMA of the plane: planes zi-1, zi accumulate, plane zi+1 is overwritten
+                  if (kc == 0) {     // first MMA of the plane: planes t-1, t accumulate, plane t+1 is overwritten
                     tc::umma_f16(col, adesc, tc_desc(b_hi, bl), id2, 1u);
                     tc::umma_f16(col + 2 * CB, adesc, tc_desc(b_hi, bl + 2 * CB), idesc1, 0u);
                   } else tc::umma_f16(col, adesc, tc_desc(b_hi, bl), id3, 1u);
@@ -207,103 +226,79 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (elected) tc::umma_commit(a_empty + 8 * a.idx);
           a.advance(SA);
         }
-        if (elected) tc::umma_commit(acc_full + 8 * done.idx);        // output plane zi-1 is complete
+        if (elected) tc::umma_commit(acc_full + 8 * done.idx);        // output plane t-1 is complete
         done.advance(R);
         ++next_done;
         __syncwarp();
         continue;
       }
-      const uint32_t run0 = min(cnt, R - lo_slot);                     // slots before the ring wraps
-      const bool single = run0 == cnt && cnt * CB <= 256;
-      // general segment list (ring wrap and/or N > 256), kept in scalars (no local-memory arrays)
-      uint32_t nseg = 0, sc0 = 0, sc1 = 0, sc2 = 0, sb0 = 0, sb1 = 0, sb2 = 0, si0 = 0, si1 = 0, si2 = 0;
-      if (!single) {
-        uint32_t i = 0;
-        while (i < cnt) {
-          const uint32_t slot = lo_slot + i < R ? lo_slot + i : lo_slot + i - R;
-          uint32_t len = min(cnt - i, R - slot);
-          len = min(len, 256u / CB);
-          const uint32_t c_ = tmem + slot * CB, b_ = (j_lo + i) * CB, d_ = idesc0 | (((len * CB) >> 3) << 17);
-          if (nseg == 0) { sc0 = c_; sb0 = b_; si0 = d_; } else if (nseg == 1) { sc1 = c_; sb1 = b_; si1 = d_; } else { sc2 = c_; sb2 = b_; si2 = d_; }
-          ++nseg; i += len;
-        }
-      }
-      const uint32_t col0 = tmem + lo_slot * CB, boff0 = j_lo * CB, idesc_s = idesc0 | (((cnt * CB) >> 3) << 17);
-      for (int kc = 0; kc < p.nkc; ++kc) {
-        DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
-        tc::tc_fence_after();
-        const uint32_t a_lo0 = ((smem_base + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
-        if (p.resident) {
-          const uint32_t b_lo_kc = b_lo_res + (uint32_t)kc * 9u * tile16;
-          if (kc == 0) {
-            // first MMA of the plane: slot by slot, overwriting (accumulate = 0) first-touched slots
-            for (uint32_t i = 0; i < cnt; ++i) {
-              const uint32_t slot = lo_slot + i < R ? lo_slot + i : lo_slot + i - R;
-              if (leader) tc::umma_f16(tmem + slot * CB, tc_desc(a_hi, a_lo0), tc_desc(b_hi, b_lo_kc + (j_lo + i) * CB), idesc1,
-                                       (zo_lo + (int)i) >= fresh_from ? 0u : 1u);
-            }
+      // ---- general path: parity classes, ring wrap, block edges, streamed weights -------------------
+      bool first_mma = true;
+      for (int c = 0; c < p.nclass; ++c) {
+        const int dlo = max(t + p.cls[c].jlo, z_lo), dhi = min(t + p.cls[c].jlo + p.cls[c].jcnt - 1, z_end - 1);
+        if (dlo > dhi) continue;
+        const uint32_t cnt = (uint32_t)(dhi - dlo + 1), r0 = (uint32_t)(dlo - (t + p.cls[c].jlo));
+        uint32_t sl = lo_slot + (uint32_t)(dlo - zo_lo);
+        if (sl >= R) sl -= R;
+        // column segments (split at the ring wrap and at N = 256), kept in scalars
+        uint32_t nseg = 0, sc0 = 0, sc1 = 0, sc2 = 0, sb0 = 0, sb1 = 0, sb2 = 0, si0 = 0, si1 = 0, si2 = 0;
+        {
+          uint32_t i = 0;
+          while (i < cnt) {
+            const uint32_t slot = sl + i < R ? sl + i : sl + i - R;
+            uint32_t len = min(cnt - i, R - slot);
+            len = min(len, 256u / CB);
+            const uint32_t c_ = tmem + slot * CB, b_ = (r0 + i) * CB, d_ = idesc0 | (((len * CB) >> 3) << 17);
+            if (nseg == 0) { sc0 = c_; sb0 = b_; si0 = d_; } else if (nseg == 1) { sc1 = c_; sb1 = b_; si1 = d_; } else { sc2 = c_; sb2 = b_; si2 = d_; }
+            ++nseg; i += len;
           }
-          if (single) {
-            if (leader) {
-              uint32_t bl = b_lo_kc + boff0;
-#pragma unroll
-              for (int sft = 0; sft < 9; ++sft) {
-#pragma unroll
-                for (int kk = 0; kk < KSTEPS; ++kk) {
-                  const uint32_t al = a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4);
-                  if (sft == 0 && kk == 0) { if (kc != 0) tc::umma_f16(col0, tc_desc(a_hi, al), tc_desc(b_hi, bl), idesc_s, 1u); }
-                  else tc::umma_f16(col0, tc_desc(a_hi, al), tc_desc(b_hi, bl + kk * kstep_b), idesc_s, 1u);
-                }
-                bl += tile16;
+        }
+        const int tapmask = p.cls[c].tapmask;
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
+          tc::tc_fence_after();
+          const uint32_t a_lo0 = ((smem_base + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+          uint32_t tile = (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0);
+          for (int m = tapmask; m; m &= m - 1, ++tile) {
+            const int sft = __ffs(m) - 1;
+            uint32_t b_lo0;
+            if (p.resident) b_lo0 = b_lo_res + tile * tile16;
+            else {
+              DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
+              tc::tc_fence_after();
+              b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+            }
+            const uint32_t a_lo1 = a_lo0 + (uint32_t)(sft / 3) * TC_PW + (uint32_t)(sft % 3);
+            if (first_mma) {
+              // first MMA of the step: slot by slot, overwriting (accumulate = 0) first-touched slots
+              for (uint32_t i = 0; i < cnt; ++i) {
+                const uint32_t slot = sl + i < R ? sl + i : sl + i - R;
+                if (leader) tc::umma_f16(tmem + slot * CB, tc_desc(a_hi, a_lo1), tc_desc(b_hi, b_lo0 + (r0 + i) * CB), idesc1,
+                                         (dlo + (int)i) >= fresh_from ? 0u : 1u);
               }
             }
-          } else if (leader) {
-            for (int sft = 0; sft < 9; ++sft)
+            if (leader) {
+#pragma unroll
               for (int kk = 0; kk < KSTEPS; ++kk) {
-                if (kc == 0 && sft == 0 && kk == 0) continue;
-                const uint64_t adesc = tc_desc(a_hi, a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4));
-                const uint32_t bl = b_lo_kc + sft * tile16 + kk * kstep_b;
+                if (kk == 0 && first_mma) continue;
+                const uint64_t adesc = tc_desc(a_hi, a_lo1 + kk * (2 * TC_PLANE_BYTES >> 4));
+                const uint32_t bl = b_lo0 + kk * kstep_b;
                 tc::umma_f16(sc0, adesc, tc_desc(b_hi, bl + sb0), si0, 1u);
                 if (nseg > 1) tc::umma_f16(sc1, adesc, tc_desc(b_hi, bl + sb1), si1, 1u);
                 if (nseg > 2) tc::umma_f16(sc2, adesc, tc_desc(b_hi, bl + sb2), si2, 1u);
               }
-          }
-        } else {
-#pragma unroll
-          for (int sft = 0; sft < 9; ++sft) {
-            DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
-            tc::tc_fence_after();
-            const uint32_t b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
-            const uint32_t a_lo1 = a_lo0 + (sft / 3) * TC_PW + (sft % 3);
-            if (sft == 0 && kc == 0) {
-              for (uint32_t i = 0; i < cnt; ++i) {
-                const uint32_t slot = lo_slot + i < R ? lo_slot + i : lo_slot + i - R;
-                if (leader) tc::umma_f16(tmem + slot * CB, tc_desc(a_hi, a_lo1), tc_desc(b_hi, b_lo0 + (j_lo + i) * CB), idesc1,
-                                         (zo_lo + (int)i) >= fresh_from ? 0u : 1u);
-              }
             }
-            if (leader) {
-#pragma unroll
-              for (int kk = 0; kk < KSTEPS; ++kk) {
-                if (sft == 0 && kk == 0 && kc == 0) continue;
-                const uint64_t adesc = tc_desc(a_hi, a_lo1 + kk * (2 * TC_PLANE_BYTES >> 4));
-                const uint32_t bl = b_lo0 + kk * kstep_b;
-                if (single) tc::umma_f16(col0, adesc, tc_desc(b_hi, bl + boff0), idesc_s, 1u);
-                else {
-                  tc::umma_f16(sc0, adesc, tc_desc(b_hi, bl + sb0), si0, 1u);
-                  if (nseg > 1) tc::umma_f16(sc1, adesc, tc_desc(b_hi, bl + sb1), si1, 1u);
-                  if (nseg > 2) tc::umma_f16(sc2, adesc, tc_desc(b_hi, bl + sb2), si2, 1u);
-                }
-              }
+            first_mma = false;
+            if (!p.resident) {
+              if (elected) tc::umma_commit(b_empty + 8 * b.idx);
+              b.advance(NB);
             }
-            if (elected) tc::umma_commit(b_empty + 8 * b.idx);
-            b.advance(NB);
           }
+          if (elected) tc::umma_commit(a_empty + 8 * a.idx);
+          a.advance(SA);
         }
-        if (elected) tc::umma_commit(a_empty + 8 * a.idx);
-        a.advance(SA);
       }
-      const int done_upto = (zi == last_zi) ? z_end - 1 : zi - 1;
+      const int done_upto = (t == last_t) ? z_end - 1 : t + p.Jlo;
       while (next_done <= done_upto) {
         if (elected) tc::umma_commit(acc_full + 8 * done.idx);
         done.advance(R);
@@ -471,33 +466,73 @@ inline uint16_t tc_to_bits(float v, bool bf16) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
+// Class order index of a voxel parity in the parity-split copy (must match tc_prepare's class loop:
+// odd D-parity first, so the first class of a step touches every freshly started output plane).
+__host__ __device__ inline int tc_s2d_class(int d, int h, int w, int sd, int sh, int sw) {
+  const int cd = sd == 2 ? 1 - (d & 1) : 0, ch = sh == 2 ? (h & 1) : 0, cw = sw == 2 ? (w & 1) : 0;
+  return (cd * sh + ch) * sw + cw;
+}
+
 // Returns 0 always; t.enabled says whether the layer runs on the tensor cores.  *why is set only on
-// a hard failure of a layer that should have been supported.
+// a hard failure of a layer that should have been supported.  For a strided layer `in0` must be the
+// parity-split copy of the producer tensor.
 inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, int cout, const int k[3], const int s[3],
                       const int in_sp[3], const int out_sp[3], int maxN, bool bf16, const void* in0, const void* in1,
                       void* out, std::string* why) {
   t.enabled = false;
   why->clear();
-  if (k[0] != 3 || k[1] != 3 || k[2] != 3 || s[0] != 1 || s[1] != 1 || s[2] != 1) return 0;
+  if (k[0] != 3 || k[1] != 3 || k[2] != 3) return 0;
+  const bool strided = s[0] != 1 || s[1] != 1 || s[2] != 1;
+  if (strided && c1 > 0) return 0;
   if (c0 % 16 || c1 % 16 || cout % 16) return 0;
-  (void)in_sp;
   const int cin = c0 + c1;
+  TcKParams& kp = t.kp;
+  // ---- parity classes ----
+  const int sd = s[0], sh = s[1], sw = s[2];
+  kp.nclass = sd * sh * sw; kp.Jlo = sd == 1 ? -1 : 0; kp.Jhi = 1; kp.jmax = sd == 1 ? 3 : 2;
+  kp.Din = in_sp[0] / sd;
+  struct Tap { int kh, kw; };
+  std::vector<std::vector<Tap>> cls_taps(kp.nclass);
+  std::vector<std::vector<int>> cls_kd(kp.nclass);
+  int tile0 = 0;
+  for (int cd = 0; cd < sd; ++cd)
+    for (int ph = 0; ph < sh; ++ph)
+      for (int pw = 0; pw < sw; ++pw) {
+        const int c = (cd * sh + ph) * sw + pw;
+        const int pd = sd == 2 ? 1 - cd : 0;
+        TcClassDesc& cd_ = kp.cls[c];
+        cd_.tapmask = 0; cd_.tile0 = tile0;
+        if (sd == 1) { cd_.jlo = -1; cd_.jcnt = 3; cls_kd[c] = {2, 1, 0}; }
+        else if (pd == 0) { cd_.jlo = 0; cd_.jcnt = 1; cls_kd[c] = {1}; }
+        else { cd_.jlo = 0; cd_.jcnt = 2; cls_kd[c] = {2, 0}; }
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx) {
+            int kh = -1, kw = -1;
+            if (sh == 1) kh = dy; else if (ph == 0) { if (dy == 1) kh = 1; } else { if (dy == 0) kh = 0; else if (dy == 1) kh = 2; }
+            if (sw == 1) kw = dx; else if (pw == 0) { if (dx == 1) kw = 1; } else { if (dx == 0) kw = 0; else if (dx == 1) kw = 2; }
+            if (kh < 0 || kw < 0) continue;
+            cd_.tapmask |= 1 << (dy * 3 + dx);
+            cls_taps[c].push_back({kh, kw});
+          }
+        tile0 += (int)cls_taps[c].size();
+      }
+  kp.tiles_per_kc = tile0;
+  // ---- tiling / shared-memory plan ----
   int KC = 64;
   while (KC > 16 && (c0 % KC || c1 % KC)) KC >>= 1;
   const int budget = TC_SMEM_MAX - TC_SMEM_RESERVED;
-  TcKParams& kp = t.kp;
   int CB = 0, SA = 0, NB = 0, resident = 0;
   for (;;) {
     const int a_stage = KC * 360;
     const int nkc = cin / KC;
-    // resident weights: largest CB >= 32 (or the whole layer) that leaves room for >= 2 activation stages
-    if (9 * nkc <= TC_MAX_NB) {
+    const int ntile = nkc * kp.tiles_per_kc;
+    if (ntile <= TC_MAX_NB) {
       for (int cbt = std::min(cout, 128); cbt >= 16; cbt -= 16) {
         if (cout % cbt) continue;
         if (cbt < 32 && cbt != cout) break;
-        const long long btot = 27LL * cin * cbt * 2;
+        const long long btot = (long long)ntile * kp.jmax * cbt * KC * 2;
         if (btot + 2LL * a_stage <= budget) {
-          CB = cbt; resident = 1; NB = 9 * nkc;
+          CB = cbt; resident = 1; NB = ntile;
           SA = (int)std::min<long long>(TC_MAX_SA, (budget - btot) / a_stage);
           break;
         }
@@ -506,7 +541,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
     if (!CB) {      // streaming weights
       for (int cbt = std::min(cout, 128); cbt >= 16; cbt -= 16) {
         if (cout % cbt) continue;
-        const int b_tile = 3 * cbt * KC * 2;
+        const int b_tile = kp.jmax * cbt * KC * 2;
         const int nb = (budget - 3 * a_stage) / b_tile;
         if (nb >= 3) { CB = cbt; resident = 0; SA = 3; NB = std::min(nb, TC_MAX_NB); break; }
       }
@@ -521,7 +556,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   kp.ncb = cout / CB; kp.SA = SA; kp.NB = NB; kp.resident = resident;
   kp.R = std::min(TC_MAX_R, 512 / CB);
   kp.fmt = bf16 ? 1 : 0;
-  kp.a_stage_bytes = KC * 360; kp.b_tile_bytes = 3 * CB * KC * 2;
+  kp.a_stage_bytes = KC * 360; kp.b_tile_bytes = kp.jmax * CB * KC * 2;
   kp.off_b = SA * kp.a_stage_bytes;
   kp.off_bar = kp.off_b + NB * kp.b_tile_bytes;
   kp.off_bar = (kp.off_bar + 127) & ~127u;
@@ -529,26 +564,30 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   if (t.smem_bytes > TC_SMEM_MAX) { *why = "internal: shared memory plan exceeds 227 KB"; return 1; }
   if (t.smem_bytes < 120 * 1024) t.smem_bytes = 120 * 1024;          // one CTA per SM: the CTA owns all 512 TMEM columns
   kp.out = out;
-  // operand tiles: [cb][kc][tap_yx][k8][row = j*CB + co][8], j = 2 - kd (output plane d-1, d, d+1)
-  const size_t tile_elems = (size_t)(KC / 8) * 3 * CB * 8;
-  std::vector<uint16_t> pk((size_t)kp.ncb * kp.nkc * 9 * tile_elems);
+  // ---- operand tiles: [cb][kc][class, tap][k8][row = r*CB + co][8]; row block r <-> output plane t+jlo+r ----
+  const size_t tile_elems = (size_t)(KC / 8) * kp.jmax * CB * 8;
+  const int ntile = kp.nkc * kp.tiles_per_kc;
+  std::vector<uint16_t> pk((size_t)kp.ncb * ntile * tile_elems, 0);
   for (int cb = 0; cb < kp.ncb; ++cb)
     for (int kc = 0; kc < kp.nkc; ++kc)
-      for (int sft = 0; sft < 9; ++sft) {
-        uint16_t* tile = pk.data() + (((size_t)cb * kp.nkc + kc) * 9 + sft) * tile_elems;
-        for (int k8 = 0; k8 < KC / 8; ++k8)
-          for (int row = 0; row < 3 * CB; ++row)
-            for (int e = 0; e < 8; ++e) {
-              const int co = cb * CB + row % CB, kd = 2 - row / CB, ci = kc * KC + k8 * 8 + e;
-              const float v = w[((size_t)co * cin + ci) * 27 + kd * 9 + sft];
-              tile[((size_t)k8 * 3 * CB + row) * 8 + e] = tc_to_bits(v, bf16);
-            }
-      }
+      for (int c = 0; c < kp.nclass; ++c)
+        for (size_t ti = 0; ti < cls_taps[c].size(); ++ti) {
+          uint16_t* tile = pk.data() + ((size_t)cb * ntile + (size_t)kc * kp.tiles_per_kc + kp.cls[c].tile0 + ti) * tile_elems;
+          for (int k8 = 0; k8 < KC / 8; ++k8)
+            for (int r = 0; r < kp.cls[c].jcnt; ++r)
+              for (int co_ = 0; co_ < CB; ++co_)
+                for (int e = 0; e < 8; ++e) {
+                  const int co = cb * CB + co_, ci = kc * KC + k8 * 8 + e;
+                  const float v = w[((size_t)co * cin + ci) * 27 + cls_kd[c][r] * 9 + cls_taps[c][ti].kh * 3 + cls_taps[c][ti].kw];
+                  tile[((size_t)k8 * kp.jmax * CB + (size_t)r * CB + co_) * 8 + e] = tc_to_bits(v, bf16);
+                }
+        }
   if (cudaMalloc(&t.wpack, pk.size() * 2) != cudaSuccess) { *why = "cudaMalloc(wpack) failed"; return 1; }
   if (cudaMemcpy(t.wpack, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy(wpack) failed"; return 1; }
   kp.wpack = t.wpack;
-  if (!tc_make_map(&t.tm0, in0, maxN, c0, kp.D, kp.H, kp.W, KC, bf16, why)) return 1;
-  if (c1 > 0) { if (!tc_make_map(&t.tm1, in1, maxN, c1, kp.D, kp.H, kp.W, KC, bf16, why)) return 1; }
+  // input maps: the (possibly parity-split) producer tensor has nclass * C0 channels at the reduced resolution
+  if (!tc_make_map(&t.tm0, in0, maxN * kp.nclass, c0, in_sp[0] / sd, in_sp[1] / sh, in_sp[2] / sw, KC, bf16, why)) return 1;
+  if (c1 > 0) { if (!tc_make_map(&t.tm1, in1, maxN, c1, in_sp[0], in_sp[1], in_sp[2], KC, bf16, why)) return 1; }
   else t.tm1 = t.tm0;
   t.enabled = true;
   return 0;

@@ -8,6 +8,8 @@
 #include "common.cuh"
 
 namespace dwmh {
+__host__ __device__ inline int tc_s2d_class(int d, int h, int w, int sd, int sh, int sw);
+
 
 // ---------------------------------------------------------------------------------------------
 // First conv (Cin == 1) fused with tile extraction + mirror flip: reads the normalised fp32 volume
@@ -200,8 +202,12 @@ __global__ void __launch_bounds__(128) conv_generic_kernel(ConvParams p) {
 // InstanceNorm (instance statistics, biased variance, eps 1e-5, affine) + LeakyReLU(0.01), in place
 // on the raw conv output.  grid.y = n * C/8 + chunk; coefficients computed once per block.
 // ---------------------------------------------------------------------------------------------
+// Optional second output: the parity-split ("space to depth") copy a strided tcgen05 conv consumes,
+// s2d[n][class][C/8][D/sd][H/sh][W/sw][8] with class order tc_s2d_class().
+struct S2dParams { void* dst; int D, H, W, sd, sh, sw; };
+
 template <typename T>
-__global__ void __launch_bounds__(256) instnorm_lrelu_kernel(void* __restrict__ y, NormParams np, int C, int64_t V) {
+__global__ void __launch_bounds__(256) instnorm_lrelu_kernel(void* __restrict__ y, NormParams np, int C, int64_t V, S2dParams sp) {
   __shared__ float sa[8], sb[8];
   const int n = blockIdx.y / (C >> 3), cc = blockIdx.y % (C >> 3);
   if (threadIdx.x < 8) { float a, b; norm_coeffs(np, n, C, cc * 8 + threadIdx.x, a, b); sa[threadIdx.x] = a; sb[threadIdx.x] = b; }
@@ -210,13 +216,23 @@ __global__ void __launch_bounds__(256) instnorm_lrelu_kernel(void* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = sa[j]; b[j] = sb[j]; }
   uint4* row = reinterpret_cast<uint4*>(y) + (size_t)blockIdx.y * V;
+  const int nclass = sp.sd * sp.sh * sp.sw;
+  const int Ds = sp.D / sp.sd, Hs = sp.H / sp.sh, Ws = sp.W / sp.sw;
+  const int64_t Vs = (int64_t)Ds * Hs * Ws;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride) {
     float f[8];
     unpack8<T>(row[v], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = lrelu(fmaf(a[j], f[j], b[j]));
-    row[v] = pack8<T>(f);
+    const uint4 o = pack8<T>(f);
+    row[v] = o;
+    if (sp.dst) {
+      const int w = (int)(v % sp.W), h = (int)((v / sp.W) % sp.H), d = (int)(v / ((int64_t)sp.W * sp.H));
+      const int c = tc_s2d_class(d, h, w, sp.sd, sp.sh, sp.sw);
+      const int64_t vs = ((int64_t)(d / sp.sd) * Hs + (h / sp.sh)) * Ws + (w / sp.sw);
+      reinterpret_cast<uint4*>(sp.dst)[(((size_t)n * nclass + c) * (C >> 3) + cc) * Vs + vs] = o;
+    }
   }
 }
 
