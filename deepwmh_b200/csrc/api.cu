@@ -318,6 +318,12 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
   for (size_t i = 0; i < c->layers.size(); ++i) {
     Layer& L = c->layers[i];
     tc_free(L.tc);
+    if (L.kind == L_TCONV) {
+      std::string why;
+      if (tc_prepare_tconv(L.tc, L.w, L.c0, L.cout, L.s, L.in_sp, maxN, c->bf16, c->layers[L.in0].out, L.out, &why))
+        if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
+      continue;
+    }
     if (L.kind != L_CONV) continue;
     const void* in0 = c->layers[L.in0].out;
     const void* in1 = L.in1 >= 0 ? c->layers[L.in1].out : nullptr;
@@ -485,6 +491,9 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
         conv_generic_kernel<T><<<grid, 128, smem, st>>>(p);
         c->launches++;
       }
+    } else if (L.tc.enabled && !c->force_generic) {
+      DW_TRY(tc_launch<T>(L.tc, nb, nullptr, c->num_sms, st, &g_err));
+      c->launches++;
     } else {
       TConvParams p;
       p.in = c->layers[L.in0].out; p.out = L.out; p.w = L.w_dev; p.N = nb; p.Cin = L.c0; p.Cout = L.cout;

@@ -52,6 +52,7 @@ struct TcKParams {
   const void* wpack; void* out; double* sums;
   int C0, C1, Cout, CB, KC, nkc, nkc0;
   int nclass, Jlo, Jhi, jmax, tiles_per_kc, Din;
+  int tconv, CBt, osd, osh, osw, Cout_t;   // transposed-conv mode: CB = osd*osh*osw * CBt, scatter epilogue
   TcClassDesc cls[8];
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
   int SA, NB, resident, R, fmt;
@@ -71,7 +72,7 @@ struct RingPos {
 __device__ __forceinline__ uint64_t tc_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
 // KSTEPS = KC/16 (UMMA K steps per channel chunk); SMALL_CB: CB <= 32 -> per-thread running statistics.
-template <typename T, int KSTEPS, bool SMALL_CB>
+template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const TcKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -104,7 +105,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     tc::fence_barrier_init();
   }
   if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_ptr_smem), 512);
-  for (int i = threadIdx.x; i < 2 * (int)CB; i += TC_THREADS) s_stat[i] = 0.f;
+  if constexpr (!TCONV) for (int i = threadIdx.x; i < 2 * (int)CB; i += TC_THREADS) s_stat[i] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -314,6 +315,37 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const bool valid = h < p.H && w < p.W && !(p.dbg & 4);
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
     const int nch = CB >> 4;
+    if constexpr (TCONV) {
+      // transposed conv (kernel == stride): column block q of the accumulator is output parity q; every
+      // input voxel (GEMM row) scatters 16-byte channel chunks to its osd*osh*osw children.
+      const int Ho = p.H * p.osh, Wo = p.W * p.osw;
+      const size_t Vo = (size_t)p.D * p.osd * Ho * Wo;
+      uint4* out_n = reinterpret_cast<uint4*>(p.out) + (size_t)n * (p.Cout_t >> 3) * Vo;
+      uint32_t slot = 0, phase = 0;
+      for (int t = z_lo; t < z_end; ++t) {
+        DWMH_TIMED_WAIT(w0_, tc::mbar_wait(acc_full + 8 * slot, phase, 7));
+        tc::tc_fence_after();
+        for (int ch = 0; ch < nch; ++ch) {
+          uint32_t r[16];
+          tc::tmem_ld16(tm_lane + slot * CB + ch * 16, r);
+          tc::tmem_ld_wait();
+          float a[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(r[i]);
+          const int col = ch * 16, qc = col / p.CBt, cofs = col - qc * p.CBt;
+          const int qa = qc / (p.osh * p.osw), qb = (qc / p.osw) % p.osh, qw = qc % p.osw;
+          if (valid) {
+            uint4* o = out_n + (size_t)((cb * p.CBt + cofs) >> 3) * Vo + ((size_t)(t * p.osd + qa) * Ho + (h * p.osh + qb)) * Wo + (w * p.osw + qw);
+            o[0] = pack8<T>(a);
+            o[Vo] = pack8<T>(a + 8);
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(acc_empty + 8 * slot);
+        if (++slot == R) { slot = 0; phase ^= 1; }
+      }
+    } else {
     constexpr int NACC = SMALL_CB ? 32 : 8;
     float rs[NACC], rq[NACC];      // SMALL_CB: per-thread per-channel running sums; else per-lane column totals
 #pragma unroll
@@ -397,6 +429,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       for (int ch = 0; ch < 8; ++ch)
         if (ch < nch) { atomicAdd(&s_stat[ch * 16 + lane], rs[ch]); atomicAdd(&s_stat[CB + ch * 16 + lane], rq[ch]); }
     }
+    }   // !TCONV
   }
   if (prof_on && lane == 0 && (warp <= 2 || warp == 6)) {
     const int role = warp == 6 ? 3 : warp;          // 0 act producer, 1 mma, 2 epilogue (warp 2), 3 weight producer
@@ -406,9 +439,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
   tc::tc_fence_before();
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * (int)CB; i += TC_THREADS) {
-    const int c = i % (int)CB, which = i / (int)CB;
-    atomicAdd(p.sums + ((size_t)n * p.Cout + (size_t)cb * CB + c) * 2 + which, (double)s_stat[i]);
+  if constexpr (!TCONV) {
+    for (int i = threadIdx.x; i < 2 * (int)CB; i += TC_THREADS) {
+      const int c = i % (int)CB, which = i / (int)CB;
+      atomicAdd(p.sums + ((size_t)n * p.Cout + (size_t)cb * CB + c) * 2 + which, (double)s_stat[i]);
+    }
   }
   if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
@@ -489,6 +524,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   TcKParams& kp = t.kp;
   // ---- parity classes ----
   const int sd = s[0], sh = s[1], sw = s[2];
+  kp.tconv = 0; kp.CBt = 0; kp.osd = kp.osh = kp.osw = 1; kp.Cout_t = cout;
   kp.nclass = sd * sh * sw; kp.Jlo = sd == 1 ? -1 : 0; kp.Jhi = 1; kp.jmax = sd == 1 ? 3 : 2;
   kp.Din = in_sp[0] / sd;
   struct Tap { int kh, kw; };
@@ -593,12 +629,76 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   return 0;
 }
 
+// Transposed conv with kernel == stride (1 or 2 per axis), no bias: a 1-tap GEMM over the INPUT voxels whose
+// N dimension stacks the osd*osh*osw output parities; w in PyTorch layout [Cin][Cout][kd][kh][kw].
+inline int tc_prepare_tconv(TcLayer& t, const std::vector<float>& w, int cin, int cout, const int s[3], const int in_sp[3],
+                            int maxN, bool bf16, const void* in0, void* out, std::string* why) {
+  t.enabled = false;
+  why->clear();
+  if (cin % 16 || cout % 16) return 0;
+  const int nco = s[0] * s[1] * s[2];
+  int CBt = 256 / nco;
+  while (CBt >= 16 && (cout % CBt || CBt % 16)) CBt -= 16;
+  if (CBt < 16) return 0;
+  TcKParams& kp = t.kp;
+  kp = TcKParams{};
+  kp.tconv = 1; kp.CBt = CBt; kp.osd = s[0]; kp.osh = s[1]; kp.osw = s[2]; kp.Cout_t = cout;
+  kp.nclass = 1; kp.Jlo = 0; kp.Jhi = 0; kp.jmax = 1; kp.tiles_per_kc = 1; kp.Din = in_sp[0];
+  kp.cls[0] = TcClassDesc{1 << 4, 0, 1, 0};
+  const int CB = nco * CBt;
+  int KC = 64;
+  while (KC > 16 && cin % KC) KC >>= 1;
+  const int budget = TC_SMEM_MAX - TC_SMEM_RESERVED;
+  const int a_stage = KC * 360, b_tile = CB * KC * 2, nkc = cin / KC;
+  int SA, NB, resident;
+  if (nkc <= TC_MAX_NB && (long long)nkc * b_tile + 2LL * a_stage <= budget) {
+    resident = 1; NB = nkc; SA = (int)std::min<long long>(TC_MAX_SA, (budget - (long long)nkc * b_tile) / a_stage);
+  } else {
+    resident = 0; SA = 3; NB = std::min((budget - 3 * a_stage) / b_tile, TC_MAX_NB);
+    if (NB < 2) return 0;
+  }
+  kp.C0 = cin; kp.C1 = 0; kp.Cout = CB * (cout / CBt); kp.CB = CB; kp.KC = KC; kp.nkc = nkc; kp.nkc0 = nkc;
+  kp.D = in_sp[0]; kp.H = in_sp[1]; kp.W = in_sp[2];
+  kp.tilesH = (kp.H + TC_TH - 1) / TC_TH; kp.tilesW = (kp.W + TC_TW - 1) / TC_TW;
+  kp.ncb = cout / CBt; kp.SA = SA; kp.NB = NB; kp.resident = resident;
+  kp.R = 512 / CB; kp.fmt = bf16 ? 1 : 0;
+  kp.a_stage_bytes = a_stage; kp.b_tile_bytes = b_tile;
+  kp.off_b = SA * a_stage;
+  kp.off_bar = (kp.off_b + NB * b_tile + 127) & ~127u;
+  t.smem_bytes = kp.off_bar + TC_SMEM_RESERVED;
+  if (t.smem_bytes > TC_SMEM_MAX) { *why = "internal: shared memory plan exceeds 227 KB"; return 1; }
+  if (t.smem_bytes < 120 * 1024) t.smem_bytes = 120 * 1024;
+  kp.out = out;
+  const int taps = nco;
+  const size_t tile_elems = (size_t)(KC / 8) * CB * 8;
+  std::vector<uint16_t> pk((size_t)kp.ncb * nkc * tile_elems, 0);
+  for (int cb = 0; cb < kp.ncb; ++cb)
+    for (int kc = 0; kc < nkc; ++kc) {
+      uint16_t* tile = pk.data() + ((size_t)cb * nkc + kc) * tile_elems;
+      for (int k8 = 0; k8 < KC / 8; ++k8)
+        for (int q = 0; q < nco; ++q)
+          for (int co_ = 0; co_ < CBt; ++co_)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = kc * KC + k8 * 8 + e, co = cb * CBt + co_;
+              tile[((size_t)k8 * CB + (size_t)q * CBt + co_) * 8 + e] = tc_to_bits(w[((size_t)ci * cout + co) * taps + q], bf16);
+            }
+    }
+  if (cudaMalloc(&t.wpack, pk.size() * 2) != cudaSuccess) { *why = "cudaMalloc(wpack) failed"; return 1; }
+  if (cudaMemcpy(t.wpack, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy(wpack) failed"; return 1; }
+  kp.wpack = t.wpack;
+  if (!tc_make_map(&t.tm0, in0, maxN, cin, in_sp[0], in_sp[1], in_sp[2], KC, bf16, why)) return 1;
+  t.tm1 = t.tm0;
+  t.enabled = true;
+  return 0;
+}
+
 template <typename T>
 inline int tc_set_attr_all() {
   cudaError_t e = cudaSuccess;
-#define DWMH_TC_ATTR(K, S) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)
-  DWMH_TC_ATTR(1, true); DWMH_TC_ATTR(2, true); DWMH_TC_ATTR(4, true);
-  DWMH_TC_ATTR(1, false); DWMH_TC_ATTR(2, false); DWMH_TC_ATTR(4, false);
+#define DWMH_TC_ATTR(K, S, C) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, K, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)
+  DWMH_TC_ATTR(1, true, false); DWMH_TC_ATTR(2, true, false); DWMH_TC_ATTR(4, true, false);
+  DWMH_TC_ATTR(1, false, false); DWMH_TC_ATTR(2, false, false); DWMH_TC_ATTR(4, false, false);
+  DWMH_TC_ATTR(1, false, true); DWMH_TC_ATTR(2, false, true); DWMH_TC_ATTR(4, false, true);
 #undef DWMH_TC_ATTR
   return e == cudaSuccess ? 0 : 1;
 }
@@ -622,10 +722,11 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   }
   kp.prof = prof_dev;
   const int ks = kp.KC / 16;
-  const bool small = kp.CB <= 32;
-#define DWMH_TC_LAUNCH(K, S) conv3_tc_kernel<T, K, S><<<grid, TC_THREADS, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
-  if (small) { if (ks == 1) DWMH_TC_LAUNCH(1, true); else if (ks == 2) DWMH_TC_LAUNCH(2, true); else DWMH_TC_LAUNCH(4, true); }
-  else { if (ks == 1) DWMH_TC_LAUNCH(1, false); else if (ks == 2) DWMH_TC_LAUNCH(2, false); else DWMH_TC_LAUNCH(4, false); }
+  const bool small = kp.CB <= 32 && !kp.tconv;
+#define DWMH_TC_LAUNCH(K, S, C) conv3_tc_kernel<T, K, S, C><<<grid, TC_THREADS, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
+  if (kp.tconv) { if (ks == 1) DWMH_TC_LAUNCH(1, false, true); else if (ks == 2) DWMH_TC_LAUNCH(2, false, true); else DWMH_TC_LAUNCH(4, false, true); }
+  else if (small) { if (ks == 1) DWMH_TC_LAUNCH(1, true, false); else if (ks == 2) DWMH_TC_LAUNCH(2, true, false); else DWMH_TC_LAUNCH(4, true, false); }
+  else { if (ks == 1) DWMH_TC_LAUNCH(1, false, false); else if (ks == 2) DWMH_TC_LAUNCH(2, false, false); else DWMH_TC_LAUNCH(4, false, false); }
 #undef DWMH_TC_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv3_tc_kernel launch failed: ") + cudaGetErrorString(e); return 1; }
