@@ -273,7 +273,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
-    ap.add_argument("--max-batch", type=int, default=8)
+    ap.add_argument("--max-batch", type=int, default=32)
     ap.add_argument("--cpu-forwards", type=int, default=3, help="tile-forwards of the bounded CPU-baseline sample (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

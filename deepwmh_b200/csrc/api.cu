@@ -55,7 +55,9 @@ struct Layer {
   std::vector<int64_t> wshape;
   bool have_w = false, have_g = false, have_b = false;
   // device
-  void* out = nullptr;              // [maxN][cout/8][V][8] T
+  void* out = nullptr;              // [maxN][cout/8][V][8] T: normalised+activated (raw for the last conv / tconv)
+  void* raw = nullptr;              // raw conv output; == out (normalised in place) unless raw32
+  bool raw32 = false;               // raw output kept in fp32 (low-resolution layers: one rounding less per layer)
   void* s2d = nullptr;              // parity-split copy for a strided tcgen05 consumer
   int s2d_s[3] = {1, 1, 1};
   float* w_dev = nullptr;           // generic packing
@@ -82,6 +84,7 @@ struct dwmh_ctx {
   std::vector<float> w_head; bool have_head = false; float* w_head_dev = nullptr;
   bool committed = false;
   bool force_generic = false;
+  int raw32_max_edge = 128;
   // workspaces
   double* stats_arena = nullptr; size_t stats_bytes = 0;
   float* probs = nullptr;            // [maxN][2][P]
@@ -184,6 +187,7 @@ extern "C" int dwmh_create(dwmh_ctx** out, int device, const dwmh_net_desc* desc
   dwmh_ctx* c = new dwmh_ctx();
   c->device = device; c->d = *desc; c->bf16 = desc->act_dtype == 1; c->num_sms = prop.multiProcessorCount;
   c->max_batch = desc->max_batch > 0 ? desc->max_batch : 8;
+  if (const char* e = getenv("DWMH_RAW32_MAX_EDGE")) c->raw32_max_edge = atoi(e);
   if (build_plan(c)) { delete c; return 1; }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
   *out = c;
@@ -196,7 +200,7 @@ extern "C" int dwmh_destroy(dwmh_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (auto& L : c->layers) { free_dev(L.out); free_dev(L.s2d); free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc); }
+  for (auto& L : c->layers) { if (L.raw != L.out) free_dev(L.raw); free_dev(L.out); free_dev(L.s2d); free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc); }
   free_dev(c->w_head_dev); free_dev(c->stats_arena); free_dev(c->probs); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
   free_dev(c->hv_vol); free_dev(c->hv_pad); free_dev(c->hv_agg); free_dev(c->hv_wgt); free_dev(c->hv_seg);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -292,6 +296,12 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     const int taps = L.k[0] * L.k[1] * L.k[2];
     if (L.has_norm) { L.sums = c->stats_arena + off; off += (size_t)maxN * L.cout * 2; }
     if (!L.out) CU_TRY(cudaMalloc(&L.out, (size_t)maxN * L.cout * L.vout() * c->elt));
+    // fp32 raw storage for low-resolution conv outputs (profiles/precision_full_r01.txt): cheap in traffic, and
+    // those layers then round once (operand) instead of twice (storage + operand)
+    L.raw32 = L.kind == L_CONV && L.has_norm && (int)(&L - c->layers.data()) != c->last_conv &&
+              std::max(L.out_sp[0], std::max(L.out_sp[1], L.out_sp[2])) <= c->raw32_max_edge;
+    if (L.raw32) { if (!L.raw || L.raw == L.out) CU_TRY(cudaMalloc(&L.raw, (size_t)maxN * L.cout * L.vout() * 4)); }
+    else L.raw = L.out;
     std::vector<float> pk;
     if (L.kind == L_FIRST) {
       pk.resize((size_t)taps * L.cout);
@@ -335,7 +345,7 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
       in0 = P.s2d;
     }
     std::string why;
-    if (tc_prepare(L.tc, L.w, L.c0, L.c1, L.cout, L.k, L.s, L.in_sp, L.out_sp, maxN, c->bf16, in0, in1, L.out, &why)) {
+    if (tc_prepare(L.tc, L.w, L.c0, L.c1, L.cout, L.k, L.s, L.in_sp, L.out_sp, maxN, c->bf16, in0, in1, L.raw, L.raw32, &why)) {
       if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
     }
   }
@@ -464,12 +474,13 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
     const int taps = L.k[0] * L.k[1] * L.k[2];
     if (L.kind == L_FIRST) {
       FirstConvParams p;
-      p.src = src; p.metas = metas; p.w = L.w_dev; p.out = L.out; p.sums = L.sums; p.patch_mode = patch_mode;
+      p.src = src; p.metas = metas; p.w = L.w_dev; p.out = L.raw; p.sums = L.sums; p.patch_mode = patch_mode;
       p.SX = SX; p.SY = SY; p.SZ = SZ; p.px = L.out_sp[0]; p.py = L.out_sp[1]; p.pz = L.out_sp[2];
       p.kd = L.k[0]; p.kh = L.k[1]; p.kw = L.k[2]; p.Cout = L.cout;
-      dim3 grid((unsigned)((L.vout() + 255) / 256), nb);
+      dim3 grid((unsigned)((L.vout() + 256 * FC_VPT - 1) / (256 * FC_VPT)), nb);
       const size_t smem = ((size_t)taps * L.cout + 2 * L.cout) * sizeof(float);
-      conv_first_kernel<T><<<grid, 256, smem, st>>>(p);
+      if (taps == 27) conv_first_kernel<T, true><<<grid, 256, smem, st>>>(p);
+      else conv_first_kernel<T, false><<<grid, 256, smem, st>>>(p);
       c->launches++;
     } else if (L.kind == L_CONV) {
       bool done = false;
@@ -481,7 +492,7 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
         ConvParams p;
         p.in0 = c->layers[L.in0].out; p.C0 = L.c0;
         p.in1 = L.in1 >= 0 ? c->layers[L.in1].out : nullptr; p.C1 = L.c1;
-        p.w = L.w_dev; p.out = L.out; p.sums = L.sums; p.N = nb;
+        p.w = L.w_dev; p.out = L.raw; p.out32 = L.raw32 ? 1 : 0; p.sums = L.sums; p.N = nb;
         p.Di = L.in_sp[0]; p.Hi = L.in_sp[1]; p.Wi = L.in_sp[2]; p.Do = L.out_sp[0]; p.Ho = L.out_sp[1]; p.Wo = L.out_sp[2];
         p.Cout = L.cout; p.kd = L.k[0]; p.kh = L.k[1]; p.kw = L.k[2]; p.sd = L.s[0]; p.sh = L.s[1]; p.sw = L.s[2];
         const int tiles = ((p.Do + GC_TD - 1) / GC_TD) * ((p.Ho + GC_TH - 1) / GC_TH) * ((p.Wo + GC_TW - 1) / GC_TW);
@@ -509,7 +520,7 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
       const int gx = (int)std::min<int64_t>((V + 255) / 256, 1024);
       dim3 grid(gx, nb * (L.cout >> 3));
       S2dParams sp{L.s2d, L.out_sp[0], L.out_sp[1], L.out_sp[2], L.s2d_s[0], L.s2d_s[1], L.s2d_s[2]};
-      instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.out, np, L.cout, V, sp);
+      instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, np, L.cout, V, sp);
       c->launches++;
     }
   }

@@ -52,6 +52,7 @@ struct TcKParams {
   const void* wpack; void* out; double* sums;
   int C0, C1, Cout, CB, KC, nkc, nkc0;
   int nclass, Jlo, Jhi, jmax, tiles_per_kc, Din;
+  int out32;                                 // raw output stored as fp32 instead of T
   int tconv, CBt, osd, osh, osw, Cout_t;   // transposed-conv mode: CB = osd*osh*osw * CBt, scatter epilogue
   TcClassDesc cls[8];
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
@@ -367,8 +368,16 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(r[i]);
           if (valid) {
-            outp[(size_t)(2 * ch) * V] = pack8<T>(a);
-            outp[(size_t)(2 * ch + 1) * V] = pack8<T>(a + 8);
+            if (p.out32) {
+              float4* o32 = reinterpret_cast<float4*>(p.out) + 2 * (size_t)(outp - reinterpret_cast<uint4*>(p.out));
+              o32[(size_t)(2 * ch) * V * 2] = make_float4(a[0], a[1], a[2], a[3]);
+              o32[(size_t)(2 * ch) * V * 2 + 1] = make_float4(a[4], a[5], a[6], a[7]);
+              o32[(size_t)(2 * ch + 1) * V * 2] = make_float4(a[8], a[9], a[10], a[11]);
+              o32[(size_t)(2 * ch + 1) * V * 2 + 1] = make_float4(a[12], a[13], a[14], a[15]);
+            } else {
+              outp[(size_t)(2 * ch) * V] = pack8<T>(a);
+              outp[(size_t)(2 * ch + 1) * V] = pack8<T>(a + 8);
+            }
           }
           if constexpr (SMALL_CB) {
             if (valid) {
@@ -513,7 +522,7 @@ __host__ __device__ inline int tc_s2d_class(int d, int h, int w, int sd, int sh,
 // parity-split copy of the producer tensor.
 inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, int cout, const int k[3], const int s[3],
                       const int in_sp[3], const int out_sp[3], int maxN, bool bf16, const void* in0, const void* in1,
-                      void* out, std::string* why) {
+                      void* out, bool out32, std::string* why) {
   t.enabled = false;
   why->clear();
   if (k[0] != 3 || k[1] != 3 || k[2] != 3) return 0;
@@ -524,6 +533,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   TcKParams& kp = t.kp;
   // ---- parity classes ----
   const int sd = s[0], sh = s[1], sw = s[2];
+  kp.out32 = out32 ? 1 : 0;
   kp.tconv = 0; kp.CBt = 0; kp.osd = kp.osh = kp.osw = 1; kp.Cout_t = cout;
   kp.nclass = sd * sh * sw; kp.Jlo = sd == 1 ? -1 : 0; kp.Jhi = 1; kp.jmax = sd == 1 ? 3 : 2;
   kp.Din = in_sp[0] / sd;
@@ -711,7 +721,7 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   kp.sums = sums;
   const int tiles = kp.tilesH * kp.tilesW;
   int ZB = kp.D;
-  while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 8) ZB = (ZB + 1) / 2;
+  while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 2) ZB = (ZB + 1) / 2;
   kp.ZB = ZB; kp.nzb = (kp.D + ZB - 1) / ZB;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DWMH_TC_DEBUG"); dbg = e ? atoi(e) : 0; } kp.dbg = dbg; }
   const unsigned grid = (unsigned)((long long)nb * kp.ncb * kp.nzb * tiles);

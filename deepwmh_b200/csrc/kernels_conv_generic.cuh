@@ -29,10 +29,16 @@ struct FirstConvParams {
   int Cout;
 };
 
-template <typename T>
+// K3: kernel is 3x3x3 (fully unrolled taps, inputs stay in registers).  Each thread walks FC_VPT voxels
+// (stride = blockDim) and keeps per-channel running statistics in registers (Cout <= 32) so the warp
+// reduction happens once per thread instead of once per voxel.
+constexpr int FC_VPT = 4;
+
+template <typename T, bool K3>
 __global__ void __launch_bounds__(256) conv_first_kernel(FirstConvParams p) {
   extern __shared__ float smf[];                 // weights [taps][Cout], then stats [Cout][2]
-  const int taps = p.kd * p.kh * p.kw;
+  const int kd = K3 ? 3 : p.kd, kh = K3 ? 3 : p.kh, kw = K3 ? 3 : p.kw;
+  const int taps = kd * kh * kw;
   float* sw = smf;
   float* sstat = smf + taps * p.Cout;
   for (int i = threadIdx.x; i < taps * p.Cout; i += blockDim.x) sw[i] = p.w[i];
@@ -40,51 +46,92 @@ __global__ void __launch_bounds__(256) conv_first_kernel(FirstConvParams p) {
   __syncthreads();
   const int n = blockIdx.y;
   const int64_t P = (int64_t)p.px * p.py * p.pz;
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = v < P;
-  const int k = (int)(v % p.pz), j = (int)((v / p.pz) % p.py), i = (int)(v / ((int64_t)p.pz * p.py));
-  float xin[27];
-  {
-    int ox = 0, oy = 0, oz = 0, flip = 0;
-    const float* src = p.src;
-    int SY = p.SY, SZ = p.SZ;
-    if (p.patch_mode) { src += (size_t)n * P; SY = p.py; SZ = p.pz; }
-    else { const SampleMeta m = p.metas[n]; ox = m.ox; oy = m.oy; oz = m.oz; flip = m.flip; }
-    int t = 0;
-    for (int a = 0; a < p.kd; ++a)
-      for (int b = 0; b < p.kh; ++b)
-        for (int c = 0; c < p.kw; ++c, ++t) {
-          const int ii = i + a - (p.kd >> 1), jj = j + b - (p.kh >> 1), kk = k + c - (p.kw >> 1);
-          float val = 0.f;
-          if (active && ii >= 0 && ii < p.px && jj >= 0 && jj < p.py && kk >= 0 && kk < p.pz) {
-            const int si = ox + ((flip & 4) ? p.px - 1 - ii : ii);
-            const int sj = oy + ((flip & 2) ? p.py - 1 - jj : jj);
-            const int sk = oz + ((flip & 1) ? p.pz - 1 - kk : kk);
-            val = __ldg(src + ((size_t)si * SY + sj) * SZ + sk);
-          }
-          xin[t] = val;
-        }
-  }
-  uint4* outp = reinterpret_cast<uint4*>(p.out) + (size_t)n * (p.Cout >> 3) * P + v;
+  int ox = 0, oy = 0, oz = 0, flip = 0;
+  const float* src = p.src;
+  int SY = p.SY, SZ = p.SZ;
+  if (p.patch_mode) { src += (size_t)n * P; SY = p.py; SZ = p.pz; }
+  else { const SampleMeta m = p.metas[n]; ox = m.ox; oy = m.oy; oz = m.oz; flip = m.flip; }
   const int lane = threadIdx.x & 31;
-  for (int cc = 0; cc < (p.Cout >> 3); ++cc) {
-    float acc[8];
+  const bool reg_stats = p.Cout <= 32;
+  float rs[32], rq[32];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-    for (int t = 0; t < taps; ++t) {
-      const float4 w0 = *reinterpret_cast<const float4*>(sw + t * p.Cout + cc * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(sw + t * p.Cout + cc * 8 + 4);
-      const float x = xin[t];
-      acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
-      acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
-    }
-    if (active) outp[(size_t)cc * P] = pack8<T>(acc);
+  for (int q = 0; q < 32; ++q) { rs[q] = 0.f; rq[q] = 0.f; }
+  for (int it = 0; it < FC_VPT; ++it) {
+    const int64_t v = ((int64_t)blockIdx.x * FC_VPT + it) * blockDim.x + threadIdx.x;
+    const bool active = v < P;
+    const int k = (int)(v % p.pz), j = (int)((v / p.pz) % p.py), i = (int)(v / ((int64_t)p.pz * p.py));
+    float xin[27];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float a = active ? acc[q] : 0.f;
-      const float s = warp_sum(a), ss = warp_sum(a * a);
-      if (lane == 0) { atomicAdd(&sstat[(cc * 8 + q) * 2], s); atomicAdd(&sstat[(cc * 8 + q) * 2 + 1], ss); }
+    for (int a = 0; a < (K3 ? 3 : 3); ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float val = 0.f;
+          if (a < kd && b < kh && c < kw) {
+            const int ii = i + a - (kd >> 1), jj = j + b - (kh >> 1), kk = k + c - (kw >> 1);
+            if (active && ii >= 0 && ii < p.px && jj >= 0 && jj < p.py && kk >= 0 && kk < p.pz) {
+              const int si = ox + ((flip & 4) ? p.px - 1 - ii : ii);
+              const int sj = oy + ((flip & 2) ? p.py - 1 - jj : jj);
+              const int sk = oz + ((flip & 1) ? p.pz - 1 - kk : kk);
+              val = __ldg(src + ((size_t)si * SY + sj) * SZ + sk);
+            }
+          }
+          xin[(a * 3 + b) * 3 + c] = val;
+        }
+    uint4* outp = reinterpret_cast<uint4*>(p.out) + (size_t)n * (p.Cout >> 3) * P + v;
+    for (int cc = 0; cc < (p.Cout >> 3); ++cc) {
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (a < kd && b < kh && c < kw) {
+              const int t = (a * kh + b) * kw + c;
+              const float4 w0 = *reinterpret_cast<const float4*>(sw + t * p.Cout + cc * 8);
+              const float4 w1 = *reinterpret_cast<const float4*>(sw + t * p.Cout + cc * 8 + 4);
+              const float x = xin[(a * 3 + b) * 3 + c];
+              acc[0] = fmaf(x, w0.x, acc[0]); acc[1] = fmaf(x, w0.y, acc[1]); acc[2] = fmaf(x, w0.z, acc[2]); acc[3] = fmaf(x, w0.w, acc[3]);
+              acc[4] = fmaf(x, w1.x, acc[4]); acc[5] = fmaf(x, w1.y, acc[5]); acc[6] = fmaf(x, w1.z, acc[6]); acc[7] = fmaf(x, w1.w, acc[7]);
+            }
+          }
+      if (active) outp[(size_t)cc * P] = pack8<T>(acc);
+      if (reg_stats) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          if (cc == q4 && active) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { rs[q4 * 8 + q] += acc[q]; rq[q4 * 8 + q] = fmaf(acc[q], acc[q], rq[q4 * 8 + q]); }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float a_ = active ? acc[q] : 0.f;
+          const float s = warp_sum(a_), ss = warp_sum(a_ * a_);
+          if (lane == 0) { atomicAdd(&sstat[(cc * 8 + q) * 2], s); atomicAdd(&sstat[(cc * 8 + q) * 2 + 1], ss); }
+        }
+      }
     }
+  }
+  if (reg_stats) {
+    // transposing butterfly: lane l ends with the warp total of channel l
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+      const bool up = (lane & k) != 0;
+#pragma unroll
+      for (int i = 0; i < k; ++i) {
+        const float sa_ = up ? rs[i] : rs[i + k], ka_ = up ? rs[i + k] : rs[i];
+        const float sb_ = up ? rq[i] : rq[i + k], kb_ = up ? rq[i + k] : rq[i];
+        rs[i] = ka_ + __shfl_xor_sync(0xffffffffu, sa_, k);
+        rq[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, k);
+      }
+    }
+    if (lane < p.Cout) { atomicAdd(&sstat[lane * 2], rs[0]); atomicAdd(&sstat[lane * 2 + 1], rq[0]); }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * p.Cout; c += blockDim.x)
@@ -103,6 +150,7 @@ struct ConvParams {
   const void* in1; int C1;
   const float* w;
   void* out;
+  int out32;                   // raw output stored as fp32 [n][Cout/8][V][8] instead of T
   double* sums;
   int N, Di, Hi, Wi, Do, Ho, Wo, Cout;
   int kd, kh, kw, sd, sh, sw;
@@ -180,12 +228,22 @@ __global__ void __launch_bounds__(128) conv_generic_kernel(ConvParams p) {
   const bool ok0 = od < p.Do && oh < p.Ho && ow < p.Wo;
   const bool ok1 = od < p.Do && oh < p.Ho && (ow + 1) < p.Wo;
   const int64_t Vo = (int64_t)p.Do * p.Ho * p.Wo;
-  uint4* outp = reinterpret_cast<uint4*>(p.out) + ((size_t)n * (p.Cout >> 3) + cob * (GC_COB >> 3)) * Vo +
-                ((size_t)od * p.Ho + oh) * p.Wo + ow;
+  const size_t obase = ((size_t)n * (p.Cout >> 3) + cob * (GC_COB >> 3)) * Vo + ((size_t)od * p.Ho + oh) * p.Wo + ow;
+  if (p.out32) {
+    float4* o32 = reinterpret_cast<float4*>(p.out);
 #pragma unroll
-  for (int q8 = 0; q8 < GC_COB / 8; ++q8) {
-    if (ok0) outp[(size_t)q8 * Vo] = pack8<T>(acc0 + q8 * 8);
-    if (ok1) outp[(size_t)q8 * Vo + 1] = pack8<T>(acc1 + q8 * 8);
+    for (int q8 = 0; q8 < GC_COB / 8; ++q8) {
+      const size_t e = (obase + (size_t)q8 * Vo) * 2;
+      if (ok0) { o32[e] = make_float4(acc0[q8 * 8], acc0[q8 * 8 + 1], acc0[q8 * 8 + 2], acc0[q8 * 8 + 3]); o32[e + 1] = make_float4(acc0[q8 * 8 + 4], acc0[q8 * 8 + 5], acc0[q8 * 8 + 6], acc0[q8 * 8 + 7]); }
+      if (ok1) { o32[e + 2] = make_float4(acc1[q8 * 8], acc1[q8 * 8 + 1], acc1[q8 * 8 + 2], acc1[q8 * 8 + 3]); o32[e + 3] = make_float4(acc1[q8 * 8 + 4], acc1[q8 * 8 + 5], acc1[q8 * 8 + 6], acc1[q8 * 8 + 7]); }
+    }
+  } else {
+    uint4* outp = reinterpret_cast<uint4*>(p.out) + obase;
+#pragma unroll
+    for (int q8 = 0; q8 < GC_COB / 8; ++q8) {
+      if (ok0) outp[(size_t)q8 * Vo] = pack8<T>(acc0 + q8 * 8);
+      if (ok1) outp[(size_t)q8 * Vo + 1] = pack8<T>(acc1 + q8 * 8);
+    }
   }
   const int lane = tid & 31;
 #pragma unroll
@@ -207,7 +265,8 @@ __global__ void __launch_bounds__(128) conv_generic_kernel(ConvParams p) {
 struct S2dParams { void* dst; int D, H, W, sd, sh, sw; };
 
 template <typename T>
-__global__ void __launch_bounds__(256) instnorm_lrelu_kernel(void* __restrict__ y, NormParams np, int C, int64_t V, S2dParams sp) {
+__global__ void __launch_bounds__(256) instnorm_lrelu_kernel(const void* __restrict__ raw, int raw32, void* __restrict__ y, NormParams np,
+                                                             int C, int64_t V, S2dParams sp) {
   __shared__ float sa[8], sb[8];
   const int n = blockIdx.y / (C >> 3), cc = blockIdx.y % (C >> 3);
   if (threadIdx.x < 8) { float a, b; norm_coeffs(np, n, C, cc * 8 + threadIdx.x, a, b); sa[threadIdx.x] = a; sb[threadIdx.x] = b; }
@@ -216,13 +275,18 @@ __global__ void __launch_bounds__(256) instnorm_lrelu_kernel(void* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = sa[j]; b[j] = sb[j]; }
   uint4* row = reinterpret_cast<uint4*>(y) + (size_t)blockIdx.y * V;
+  const uint4* rrow = reinterpret_cast<const uint4*>(raw) + (size_t)blockIdx.y * V;
+  const float4* rrow32 = reinterpret_cast<const float4*>(raw) + (size_t)blockIdx.y * V * 2;
   const int nclass = sp.sd * sp.sh * sp.sw;
   const int Ds = sp.D / sp.sd, Hs = sp.H / sp.sh, Ws = sp.W / sp.sw;
   const int64_t Vs = (int64_t)Ds * Hs * Ws;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride) {
     float f[8];
-    unpack8<T>(row[v], f);
+    if (raw32) {
+      const float4 lo = rrow32[2 * v], hi = rrow32[2 * v + 1];
+      f[0] = lo.x; f[1] = lo.y; f[2] = lo.z; f[3] = lo.w; f[4] = hi.x; f[5] = hi.y; f[6] = hi.z; f[7] = hi.w;
+    } else unpack8<T>(rrow[v], f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = lrelu(fmaf(a[j], f[j], b[j]));
     const uint4 o = pack8<T>(f);
