@@ -110,7 +110,7 @@ def run_reference(args):
     times = cpu_forward_sample(args.warmup + args.steps, cores)[args.warmup:]
     per_fwd = sum(times) / len(times)
     vps = 1.0 / (per_fwd * N_TILES * N_MIRRORS)
-    sample = "each step = 1 of the 96 tile-forwards (128^3 patch, mirror m=step%8, softmax, x Gaussian/8) of the workload, fp32 oracle, torch CPU %d threads; volumes/s = 1/(96 x s per forward)" % cores
+    sample = "each step = 1 of the 96 tile-forwards (128^3 patch, mirror m = step mod 8, softmax, x Gaussian/8) of the workload, fp32 oracle, torch CPU %d threads; volumes/s = 1/(96 x s per forward)" % cores
     print(json.dumps({
         "impl": "reference", "metric": "volumes/sec", "value": vps, "unit": "volumes/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_fwd * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -210,7 +210,9 @@ def run_b200(args):
     st = (C.c_float * 4)()
     n._lib.dwmh_get_stage_timing(n._ctx, st)
     n._lib.dwmh_set_stage_timing(n._ctx, 0)
-    conv_ms, agg_ms = float(st[0]), float(st[1])
+    conv_ms, agg_ms, tc_ms, tc_tflop = float(st[0]), float(st[1]), float(st[2]), float(st[3])
+    kinds_all = [n.layer_kernel_kind(i) for i in range(n.num_layers())]
+    tc_launches_per_fwd = int(sum(kinds_all))
     # HBM-bound kernels timed alone
     def ev_time(fn, reps=5):
         fn(); torch.cuda.synchronize()
@@ -231,7 +233,9 @@ def run_b200(args):
     vps = world * args.steps / (ms_dev / 1e3)
     vps_e2e = world * max(1, args.steps) / (ms_e2e / 1e3)
     tflop_vol = flops_fwd * N_TILES * N_MIRRORS / 1e12
-    achieved = tflop_vol / (conv_ms / 1e3)
+    n_batches = -(-N_TILES * N_MIRRORS // args.max_batch)
+    tc_launches = tc_launches_per_fwd * n_batches
+    achieved = tc_tflop / (tc_ms / 1e3)            # dominant kernel: conv3_tc_kernel (all tcgen05 conv / tconv launches)
     # bounded CPU sample: 3 tile-forwards of the same workload on all host cores
     cores = os.cpu_count()
     cpu_t = cpu_forward_sample(1 + args.cpu_forwards, cores)[1:] if args.cpu_forwards > 0 else []
@@ -251,8 +255,11 @@ def run_b200(args):
                    "l2": "192 MiB flush buffer written between steps; per-batch activation working set (~7 GB) >> 126 MB L2",
                    "tcgen05_layers": int(sum(kinds)), "direct_layers": int(len(kinds) - sum(kinds))},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
-                     "traffic": None, "kernel": "conv stack (all conv3d/transposed-conv/head launches of the 96 forwards)",
-                     "conv_stack_ms_per_volume": conv_ms, "aggregate_ms_per_volume": agg_ms, "peak_source": pk["src"] + ", sustained bf16; burst %.1f" % pk["tensor_burst"]},
+                     "traffic": None, "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM conv3d / strided conv / transposed conv)",
+                     "launches_per_volume": tc_launches, "avg_launch_ms": tc_ms / max(tc_launches, 1), "tflop_per_volume_in_kernel": tc_tflop,
+                     "kernel_ms_per_volume": tc_ms, "kernel_share_of_step": tc_ms / (ms_dev / args.steps),
+                     "conv_stack_ms_per_volume": conv_ms, "conv_stack_tflops": tflop_vol / (conv_ms / 1e3), "aggregate_ms_per_volume": agg_ms,
+                     "peak_source": pk["src"] + ": sustained bf16 cuBLAS (the kernel runs inside a long step); burst %.1f" % pk["tensor_burst"]},
         "hbm_kernels": {"zscore": {"ms": zs_ms, "GBps": 12.0 * V / 1e9 / (zs_ms / 1e3), "frac_of_measured_hbm": 12.0 * V / 1e9 / (zs_ms / 1e3) / pk["hbm"]},
                         "finalize": {"ms": fin_ms, "GBps": 21.0 * V / 1e9 / (fin_ms / 1e3), "frac_of_measured_hbm": 21.0 * V / 1e9 / (fin_ms / 1e3) / pk["hbm"]},
                         "note": "volume (87 MB / 152 MB algorithmic) fits the 126 MB L2 only partly; timed with an L2 flush before each launch"},

@@ -98,6 +98,7 @@ struct dwmh_ctx {
   int64_t launches = 0; double conv_flops = 0.0;
   bool stage_timing = false; float stage_ms[4] = {0, 0, 0, 0};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> tcev; int tcev_used = 0; double tc_ms = 0.0, tc_flops = 0.0, tc_launches = 0.0;   // per-launch timing of the tcgen05 kernel (stage timing only)
   int num_sms = 148;
   int64_t P() const { return (int64_t)d.patch_size[0] * d.patch_size[1] * d.patch_size[2]; }
 };
@@ -204,6 +205,7 @@ extern "C" int dwmh_destroy(dwmh_ctx* c) {
   free_dev(c->w_head_dev); free_dev(c->stats_arena); free_dev(c->probs); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
   free_dev(c->hv_vol); free_dev(c->hv_pad); free_dev(c->hv_agg); free_dev(c->hv_wgt); free_dev(c->hv_seg);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (auto e : c->tcev) cudaEventDestroy(e);
   delete c;
   return 0;
 }
@@ -485,7 +487,10 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
     } else if (L.kind == L_CONV) {
       bool done = false;
       if (L.tc.enabled && !c->force_generic) {
+        const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
+        if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
         DW_TRY(tc_launch<T>(L.tc, nb, L.sums, c->num_sms, st, &g_err));
+        if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
         done = true; c->launches++;
       }
       if (!done) {
@@ -503,7 +508,10 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
         c->launches++;
       }
     } else if (L.tc.enabled && !c->force_generic) {
+      const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
+      if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
       DW_TRY(tc_launch<T>(L.tc, nb, nullptr, c->num_sms, st, &g_err));
+      if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
       c->launches++;
     } else {
       TConvParams p;
@@ -626,6 +634,10 @@ extern "C" int dwmh_predict_3d(dwmh_ctx* c, const float* vol, int32_t X, int32_t
   const int tiles_per_batch = std::max(1, c->max_batch / M);
   const int64_t P = c->P();
   float conv_ms = 0.f, agg_ms = 0.f;
+  if (c->stage_timing) {
+    while (c->tcev.size() < 128) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); c->tcev.push_back(e); }
+    c->tcev_used = 0; c->tc_ms = 0; c->tc_flops = 0; c->tc_launches = 0;
+  }
   for (int t0 = 0; t0 < nt; t0 += tiles_per_batch) {
     const int tb = std::min(tiles_per_batch, nt - t0);
     if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[0], st));
@@ -643,10 +655,12 @@ extern "C" int dwmh_predict_3d(dwmh_ctx* c, const float* vol, int32_t X, int32_t
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
       conv_ms += a; agg_ms += b;
+      for (int i = 0; i + 1 < c->tcev_used; i += 2) { float t = 0; cudaEventElapsedTime(&t, c->tcev[i], c->tcev[i + 1]); c->tc_ms += t; }
+      c->tcev_used = 0;
     }
   }
   CU_TRY(cudaGetLastError());
-  if (c->stage_timing) { c->stage_ms[0] = conv_ms; c->stage_ms[1] = agg_ms; }
+  if (c->stage_timing) { c->stage_ms[0] = conv_ms; c->stage_ms[1] = agg_ms; c->stage_ms[2] = (float)c->tc_ms; c->stage_ms[3] = (float)(c->tc_flops / 1e12); }
   return 0;
 }
 

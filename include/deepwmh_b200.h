@@ -119,7 +119,8 @@ int dwmh_set_force_generic(dwmh_ctx* ctx, int32_t on);
 /* Counters since creation: kernels launched by this library, conv FLOPs issued. */
 int dwmh_get_counters(dwmh_ctx* ctx, int64_t* kernel_launches, double* conv_flops);
 /* Device time (ms, CUDA events on `stream`) the last dwmh_predict_3d spent per stage:
- * out[0]=conv stack, out[1]=head+aggregate.  Only filled when profiling was enabled (adds syncs). */
+ * out[0]=conv stack (all kernels of the forwards), out[1]=aggregate, out[2]=sum of the tcgen05 conv kernel launches
+ * (CUDA events around every launch), out[3]=TFLOP those launches computed.  Only filled when enabled (adds syncs). */
 int dwmh_set_stage_timing(dwmh_ctx* ctx, int32_t on);
 int dwmh_get_stage_timing(dwmh_ctx* ctx, float out_ms[4]);
 
