@@ -72,6 +72,18 @@ struct Layer {
   }
 };
 
+// One independent forward pipeline: its own activation buffers, statistics, probabilities, tensor maps and
+// stream.  HBM-bound kernels (norm, first conv, head) of one lane overlap with tensor-bound kernels of another.
+struct LaneLayer { void* out = nullptr; void* raw = nullptr; void* s2d = nullptr; double* sums = nullptr; CUtensorMap tm0, tm1; };
+struct Lane {
+  std::vector<LaneLayer> ll;
+  double* stats_arena = nullptr; float* probs = nullptr;
+  cudaStream_t stream = nullptr;      // tensor-core kernels (low priority)
+  cudaStream_t stream_aux = nullptr;  // HBM / CUDA-core kernels (high priority): slot in beside another lane's tcgen05 CTAs
+  std::vector<cudaEvent_t> hop; int hop_i = 0;
+  cudaEvent_t fwd_done = nullptr, agg_done = nullptr; bool agg_pending = false;
+};
+
 struct dwmh_ctx {
   int device = 0;
   dwmh_net_desc d{};
@@ -86,8 +98,9 @@ struct dwmh_ctx {
   bool force_generic = false;
   int raw32_max_edge = 128;
   // workspaces
-  double* stats_arena = nullptr; size_t stats_bytes = 0;
+  double* stats_arena = nullptr; size_t stats_bytes = 0;   // views of the active lane
   float* probs = nullptr;            // [maxN][2][P]
+  std::vector<Lane> lanes; int nlanes = 1; int active_lane = -1; cudaEvent_t ev_start = nullptr; bool split_streams = false;
   float* gauss_dev = nullptr; std::vector<float> gauss_host; bool gauss_custom = false;
   SampleMeta* metas_dev = nullptr; size_t metas_cap = 0;
   double* zs_acc = nullptr;
@@ -189,6 +202,9 @@ extern "C" int dwmh_create(dwmh_ctx** out, int device, const dwmh_net_desc* desc
   c->device = device; c->d = *desc; c->bf16 = desc->act_dtype == 1; c->num_sms = prop.multiProcessorCount;
   c->max_batch = desc->max_batch > 0 ? desc->max_batch : 8;
   if (const char* e = getenv("DWMH_RAW32_MAX_EDGE")) c->raw32_max_edge = atoi(e);
+  c->nlanes = desc->lanes > 0 ? desc->lanes : 1;
+  if (const char* e = getenv("DWMH_LANES")) c->nlanes = std::max(1, atoi(e));
+  if (const char* e = getenv("DWMH_SPLIT_STREAMS")) c->split_streams = atoi(e) != 0;
   if (build_plan(c)) { delete c; return 1; }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
   *out = c;
@@ -201,8 +217,18 @@ extern "C" int dwmh_destroy(dwmh_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (auto& L : c->layers) { if (L.raw != L.out) free_dev(L.raw); free_dev(L.out); free_dev(L.s2d); free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc); }
-  free_dev(c->w_head_dev); free_dev(c->stats_arena); free_dev(c->probs); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
+  for (auto& ln : c->lanes) {
+    for (auto& b : ln.ll) { if (b.raw != b.out) free_dev(b.raw); free_dev(b.out); free_dev(b.s2d); }
+    free_dev(ln.stats_arena); free_dev(ln.probs);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+    if (ln.stream_aux) cudaStreamDestroy(ln.stream_aux);
+    for (auto e : ln.hop) cudaEventDestroy(e);
+    if (ln.fwd_done) cudaEventDestroy(ln.fwd_done);
+    if (ln.agg_done) cudaEventDestroy(ln.agg_done);
+  }
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  for (auto& L : c->layers) { free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc); }
+  free_dev(c->w_head_dev); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
   free_dev(c->hv_vol); free_dev(c->hv_pad); free_dev(c->hv_agg); free_dev(c->hv_wgt); free_dev(c->hv_seg);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (auto e : c->tcev) cudaEventDestroy(e);
@@ -289,21 +315,14 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     if (L.has_norm && (!L.have_g || !L.have_b)) return fail("missing instnorm parameters for %s", L.name.c_str());
   }
   const int maxN = c->max_batch;
-  // stats arena
-  size_t stat_doubles = 0;
-  for (auto& L : c->layers) if (L.has_norm) stat_doubles += (size_t)maxN * L.cout * 2;
-  if (!c->stats_arena) { c->stats_bytes = stat_doubles * sizeof(double); CU_TRY(cudaMalloc((void**)&c->stats_arena, c->stats_bytes)); }
-  size_t off = 0;
+  const int nL = (int)c->layers.size();
+  // ---- shared: weight packing for the CUDA-core kernels, norm parameters ----
   for (auto& L : c->layers) {
     const int taps = L.k[0] * L.k[1] * L.k[2];
-    if (L.has_norm) { L.sums = c->stats_arena + off; off += (size_t)maxN * L.cout * 2; }
-    if (!L.out) CU_TRY(cudaMalloc(&L.out, (size_t)maxN * L.cout * L.vout() * c->elt));
-    // fp32 raw storage for low-resolution conv outputs (profiles/precision_full_r01.txt): cheap in traffic, and
-    // those layers then round once (operand) instead of twice (storage + operand)
+    // fp32 raw storage of conv outputs (profiles/precision_full_r01.txt): those layers then round once
+    // (operand) instead of twice (storage + operand)
     L.raw32 = L.kind == L_CONV && L.has_norm && (int)(&L - c->layers.data()) != c->last_conv &&
               std::max(L.out_sp[0], std::max(L.out_sp[1], L.out_sp[2])) <= c->raw32_max_edge;
-    if (L.raw32) { if (!L.raw || L.raw == L.out) CU_TRY(cudaMalloc(&L.raw, (size_t)maxN * L.cout * L.vout() * 4)); }
-    else L.raw = L.out;
     std::vector<float> pk;
     if (L.kind == L_FIRST) {
       pk.resize((size_t)taps * L.cout);
@@ -326,32 +345,70 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     if (L.has_norm) { DW_TRY(upload(&L.gamma_dev, L.gamma)); DW_TRY(upload(&L.beta_dev, L.beta)); }
   }
   DW_TRY(upload(&c->w_head_dev, c->w_head));
-  // tcgen05 packing for the layer shapes it supports
-  for (size_t i = 0; i < c->layers.size(); ++i) {
-    Layer& L = c->layers[i];
-    tc_free(L.tc);
-    if (L.kind == L_TCONV) {
-      std::string why;
-      if (tc_prepare_tconv(L.tc, L.w, L.c0, L.cout, L.s, L.in_sp, maxN, c->bf16, c->layers[L.in0].out, L.out, &why))
-        if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
-      continue;
-    }
-    if (L.kind != L_CONV) continue;
-    const void* in0 = c->layers[L.in0].out;
-    const void* in1 = L.in1 >= 0 ? c->layers[L.in1].out : nullptr;
+  // which producers need a parity-split copy (strided tcgen05 consumer)
+  for (auto& L : c->layers) {
     const bool strided = L.s[0] != 1 || L.s[1] != 1 || L.s[2] != 1;
-    if (strided && L.k[0] == 3 && L.k[1] == 3 && L.k[2] == 3 && L.c0 % 16 == 0 && L.c1 == 0 && L.cout % 16 == 0) {
-      Layer& P = c->layers[L.in0];
-      if (!P.s2d) CU_TRY(cudaMalloc(&P.s2d, (size_t)maxN * P.cout * P.vout() * c->elt));
-      for (int a_ = 0; a_ < 3; ++a_) P.s2d_s[a_] = L.s[a_];
-      in0 = P.s2d;
-    }
-    std::string why;
-    if (tc_prepare(L.tc, L.w, L.c0, L.c1, L.cout, L.k, L.s, L.in_sp, L.out_sp, maxN, c->bf16, in0, in1, L.raw, L.raw32, &why)) {
-      if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
+    if (L.kind == L_CONV && strided && L.k[0] == 3 && L.k[1] == 3 && L.k[2] == 3 && L.c0 % 16 == 0 && L.c1 == 0 && L.cout % 16 == 0)
+      for (int a_ = 0; a_ < 3; ++a_) c->layers[L.in0].s2d_s[a_] = L.s[a_];
+  }
+  // ---- per lane: activation buffers, statistics, probabilities ----
+  size_t stat_doubles = 0;
+  for (auto& L : c->layers) if (L.has_norm) stat_doubles += (size_t)maxN * L.cout * 2;
+  c->stats_bytes = stat_doubles * sizeof(double);
+  if (c->lanes.empty()) {
+    c->lanes.resize(c->nlanes);
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
+    for (auto& ln : c->lanes) {
+      ln.ll.resize(nL);
+      int prio_lo = 0, prio_hi = 0;
+      CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      CU_TRY(cudaStreamCreateWithPriority(&ln.stream, cudaStreamNonBlocking, prio_lo));
+      CU_TRY(cudaStreamCreateWithPriority(&ln.stream_aux, cudaStreamNonBlocking, prio_hi));
+      ln.hop.resize(64);
+      for (auto& e : ln.hop) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&ln.fwd_done, cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&ln.agg_done, cudaEventDisableTiming));
+      CU_TRY(cudaMalloc((void**)&ln.stats_arena, c->stats_bytes));
+      CU_TRY(cudaMalloc((void**)&ln.probs, (size_t)maxN * 2 * c->P() * sizeof(float)));
+      size_t off = 0;
+      for (int i = 0; i < nL; ++i) {
+        Layer& L = c->layers[i];
+        LaneLayer& b = ln.ll[i];
+        if (L.has_norm) { b.sums = ln.stats_arena + off; off += (size_t)maxN * L.cout * 2; }
+        CU_TRY(cudaMalloc(&b.out, (size_t)maxN * L.cout * L.vout() * c->elt));
+        if (L.raw32) CU_TRY(cudaMalloc(&b.raw, (size_t)maxN * L.cout * L.vout() * 4)); else b.raw = b.out;
+        const bool need_s2d = L.s2d_s[0] * L.s2d_s[1] * L.s2d_s[2] > 1;
+        if (need_s2d) CU_TRY(cudaMalloc(&b.s2d, (size_t)maxN * L.cout * L.vout() * c->elt));
+      }
     }
   }
-  if (!c->probs) CU_TRY(cudaMalloc((void**)&c->probs, (size_t)maxN * 2 * c->P() * sizeof(float)));
+  // ---- tcgen05 packing (shared) + tensor maps (per lane) ----
+  for (int li = 0; li < (int)c->lanes.size(); ++li) {
+    Lane& ln = c->lanes[li];
+    for (int i = 0; i < nL; ++i) {
+      Layer& L = c->layers[i];
+      LaneLayer& b = ln.ll[i];
+      if (L.kind == L_FIRST) continue;
+      const void* in0 = ln.ll[L.in0].out;
+      const void* in1 = L.in1 >= 0 ? ln.ll[L.in1].out : nullptr;
+      const bool strided = L.kind == L_CONV && (L.s[0] != 1 || L.s[1] != 1 || L.s[2] != 1);
+      if (strided && ln.ll[L.in0].s2d) in0 = ln.ll[L.in0].s2d;
+      std::string why;
+      if (li == 0) {
+        tc_free(L.tc);
+        if (L.kind == L_TCONV) {
+          if (tc_prepare_tconv(L.tc, L.w, L.c0, L.cout, L.s, L.in_sp, maxN, c->bf16, in0, b.out, &why))
+            if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
+        } else if (tc_prepare(L.tc, L.w, L.c0, L.c1, L.cout, L.k, L.s, L.in_sp, L.out_sp, maxN, c->bf16, in0, in1, b.raw, L.raw32, &why)) {
+          if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
+        }
+      } else if (L.tc.enabled) {
+        if (tc_remap(L.tc, in0, in1, &why)) return fail("tcgen05 tensor maps for %s failed: %s", L.name.c_str(), why.c_str());
+      }
+      b.tm0 = L.tc.tm0; b.tm1 = L.tc.tm1;
+    }
+  }
+  c->active_lane = -1;
   if (!c->zs_acc) CU_TRY(cudaMalloc((void**)&c->zs_acc, 4 * sizeof(double)));
   if (!c->gauss_custom) {
     c->gauss_host.resize(c->P());
@@ -368,6 +425,24 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     CU_TRY(cudaFuncSetAttribute(tconv_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   }
   DW_TRY(tc_init_attributes(c->bf16));
+  // The tcgen05 CTA runs with the maximum shared-memory carveout; kernels meant to run BESIDE it on the same SM
+  // (other lane, high-priority stream) must ask for the same carveout or the SM has to drain to reconfigure.
+  {
+    const int mx = cudaSharedmemCarveoutMaxShared;
+    if (c->bf16) {
+      cudaFuncSetAttribute(instnorm_lrelu_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+      cudaFuncSetAttribute(conv_first_kernel<__nv_bfloat16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+      cudaFuncSetAttribute(conv_first_kernel<__nv_bfloat16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+      cudaFuncSetAttribute(head_softmax_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    } else {
+      cudaFuncSetAttribute(instnorm_lrelu_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+      cudaFuncSetAttribute(conv_first_kernel<__half, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+      cudaFuncSetAttribute(conv_first_kernel<__half, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+      cudaFuncSetAttribute(head_softmax_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    }
+    cudaFuncSetAttribute(aggregate_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+    cudaGetLastError();
+  }
   c->committed = true;
   return 0;
 }
@@ -466,15 +541,47 @@ extern "C" int dwmh_zscore(dwmh_ctx* c, float* vol, const int8_t* seg, int64_t n
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// Point the layer structs at one lane's buffers / tensor maps (kernel parameters are captured by value at
+// launch, so switching views between launches on the host is safe).
+static void activate_lane(dwmh_ctx* c, int lane) {
+  if (c->active_lane == lane) return;
+  Lane& ln = c->lanes[lane];
+  for (size_t i = 0; i < c->layers.size(); ++i) {
+    Layer& L = c->layers[i];
+    const LaneLayer& b = ln.ll[i];
+    L.out = b.out; L.raw = b.raw; L.s2d = b.s2d; L.sums = b.sums;
+    if (L.tc.enabled) { L.tc.tm0 = b.tm0; L.tc.tm1 = b.tm1; L.tc.kp.out = L.kind == L_TCONV ? b.out : b.raw; }
+  }
+  c->stats_arena = ln.stats_arena; c->probs = ln.probs;
+  c->active_lane = lane;
+}
+
+// Issue-stream selection inside one forward: `tc` kernels go to st_tc, everything else to st_aux; when the
+// two differ, consecutive kernels are chained with an event (record on the previous stream, wait on the next).
+struct StreamHop {
+  cudaStream_t st_tc, st_aux, cur; Lane* ln;
+  int to(cudaStream_t want) {
+    if (want == cur) return 0;
+    cudaEvent_t e = ln->hop[ln->hop_i]; ln->hop_i = (ln->hop_i + 1) % (int)ln->hop.size();
+    if (cudaEventRecord(e, cur) != cudaSuccess || cudaStreamWaitEvent(want, e, 0) != cudaSuccess) return 1;
+    cur = want;
+    return 0;
+  }
+};
+
 template <typename T>
 static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, int SY, int SZ,
-                        const SampleMeta* metas, int nb, cudaStream_t st) {
+                        const SampleMeta* metas, int nb, cudaStream_t st_tc, cudaStream_t st_aux, Lane* lane, cudaStream_t* last) {
   if (nb > c->max_batch) return fail("forward: batch %d > max_batch %d", nb, c->max_batch);
+  StreamHop hop{st_tc, st_aux, st_aux, lane};
+  cudaStream_t st = st_aux;
   CU_TRY(cudaMemsetAsync(c->stats_arena, 0, c->stats_bytes, st));
   for (size_t li = 0; li < c->layers.size(); ++li) {
     Layer& L = c->layers[li];
     const int taps = L.k[0] * L.k[1] * L.k[2];
     if (L.kind == L_FIRST) {
+      if (hop.to(st_aux)) return fail("stream hop failed");
+      st = st_aux;
       FirstConvParams p;
       p.src = src; p.metas = metas; p.w = L.w_dev; p.out = L.raw; p.sums = L.sums; p.patch_mode = patch_mode;
       p.SX = SX; p.SY = SY; p.SZ = SZ; p.px = L.out_sp[0]; p.py = L.out_sp[1]; p.pz = L.out_sp[2];
@@ -487,6 +594,8 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
     } else if (L.kind == L_CONV) {
       bool done = false;
       if (L.tc.enabled && !c->force_generic) {
+        if (hop.to(st_tc)) return fail("stream hop failed");
+        st = st_tc;
         const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
         if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
         DW_TRY(tc_launch<T>(L.tc, nb, L.sums, c->num_sms, st, &g_err));
@@ -494,6 +603,8 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
         done = true; c->launches++;
       }
       if (!done) {
+        if (hop.to(st_aux)) return fail("stream hop failed");
+        st = st_aux;
         ConvParams p;
         p.in0 = c->layers[L.in0].out; p.C0 = L.c0;
         p.in1 = L.in1 >= 0 ? c->layers[L.in1].out : nullptr; p.C1 = L.c1;
@@ -508,12 +619,16 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
         c->launches++;
       }
     } else if (L.tc.enabled && !c->force_generic) {
+      if (hop.to(st_tc)) return fail("stream hop failed");
+      st = st_tc;
       const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
       if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
       DW_TRY(tc_launch<T>(L.tc, nb, nullptr, c->num_sms, st, &g_err));
       if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
       c->launches++;
     } else {
+      if (hop.to(st_aux)) return fail("stream hop failed");
+      st = st_aux;
       TConvParams p;
       p.in = c->layers[L.in0].out; p.out = L.out; p.w = L.w_dev; p.N = nb; p.Cin = L.c0; p.Cout = L.cout;
       p.Di = L.in_sp[0]; p.Hi = L.in_sp[1]; p.Wi = L.in_sp[2]; p.sd = L.s[0]; p.sh = L.s[1]; p.sw = L.s[2];
@@ -523,6 +638,8 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
     }
     c->conv_flops += L.flops_per_sample() * nb;
     if (L.has_norm && (int)li != c->last_conv) {
+      if (hop.to(st_aux)) return fail("stream hop failed");
+      st = st_aux;
       NormParams np{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
       const int64_t V = L.vout();
       const int gx = (int)std::min<int64_t>((V + 255) / 256, 1024);
@@ -533,6 +650,8 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
     }
   }
   // head: norm-on-load + 1x1x1 + softmax
+  if (hop.to(st_aux)) return fail("stream hop failed");
+  st = st_aux;
   Layer& L = c->layers[c->last_conv];
   NormParams np{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
   dim3 grid((unsigned)((L.vout() + 255) / 256), nb);
@@ -540,12 +659,16 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
   c->launches++;
   c->conv_flops += 2.0 * L.vout() * L.cout * c->d.num_classes * nb;
   CU_TRY(cudaGetLastError());
+  if (last) *last = hop.cur;
   return 0;
 }
 
-static int forward(dwmh_ctx* c, const float* src, int patch_mode, int SX, int SY, int SZ, const SampleMeta* metas, int nb, cudaStream_t st) {
-  return c->bf16 ? forward_impl<__nv_bfloat16>(c, src, patch_mode, SX, SY, SZ, metas, nb, st)
-                 : forward_impl<__half>(c, src, patch_mode, SX, SY, SZ, metas, nb, st);
+// single-stream form (hooks) and two-stream form (lanes)
+static int forward(dwmh_ctx* c, const float* src, int patch_mode, int SX, int SY, int SZ, const SampleMeta* metas, int nb,
+                   cudaStream_t st_tc, cudaStream_t st_aux = nullptr, Lane* lane = nullptr, cudaStream_t* last = nullptr) {
+  if (!lane) st_aux = st_tc;
+  return c->bf16 ? forward_impl<__nv_bfloat16>(c, src, patch_mode, SX, SY, SZ, metas, nb, st_tc, st_aux, lane, last)
+                 : forward_impl<__half>(c, src, patch_mode, SX, SY, SZ, metas, nb, st_tc, st_aux, lane, last);
 }
 
 extern "C" int dwmh_forward_patches(dwmh_ctx* c, const float* patches, int32_t n, float* probs_out, void* stream_) {
@@ -554,6 +677,7 @@ extern "C" int dwmh_forward_patches(dwmh_ctx* c, const float* patches, int32_t n
   cudaStream_t st = (cudaStream_t)stream_;
   CU_TRY(cudaSetDevice(c->device));
   const int64_t P = c->P();
+  activate_lane(c, 0);
   for (int b = 0; b < n; b += c->max_batch) {
     const int nb = std::min(c->max_batch, n - b);
     DW_TRY(forward(c, patches + (size_t)b * P, 1, 0, 0, 0, nullptr, nb, st));
@@ -564,6 +688,7 @@ extern "C" int dwmh_forward_patches(dwmh_ctx* c, const float* patches, int32_t n
 
 extern "C" int dwmh_debug_layer_output(dwmh_ctx* c, int32_t li, float* out, int64_t capacity, int32_t dims[5], void* stream_) {
   if (!c || li < 0 || li >= (int)c->layers.size()) return fail("dwmh_debug_layer_output: bad layer index");
+  activate_lane(c, 0);
   Layer& L = c->layers[li];
   const int n = c->max_batch;
   dims[0] = n; dims[1] = L.cout; dims[2] = L.out_sp[0]; dims[3] = L.out_sp[1]; dims[4] = L.out_sp[2];
@@ -638,22 +763,43 @@ extern "C" int dwmh_predict_3d(dwmh_ctx* c, const float* vol, int32_t X, int32_t
     while (c->tcev.size() < 128) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); c->tcev.push_back(e); }
     c->tcev_used = 0; c->tc_ms = 0; c->tc_flops = 0; c->tc_launches = 0;
   }
-  for (int t0 = 0; t0 < nt; t0 += tiles_per_batch) {
+  // Lanes: batch b runs its forwards on lane (b % nlanes)'s stream; the overlap-add of every tile is issued on
+  // the caller's stream in tile order (deterministic).  Profiling mode serialises everything on one lane.
+  const int nl = c->stage_timing ? 1 : (int)c->lanes.size();
+  CU_TRY(cudaEventRecord(c->ev_start, st));
+  for (int l = 0; l < nl; ++l) {
+    CU_TRY(cudaStreamWaitEvent(c->lanes[l].stream, c->ev_start, 0));
+    CU_TRY(cudaStreamWaitEvent(c->lanes[l].stream_aux, c->ev_start, 0));
+    c->lanes[l].agg_pending = false;
+  }
+  int bi = 0;
+  for (int t0 = 0; t0 < nt; t0 += tiles_per_batch, ++bi) {
     const int tb = std::min(tiles_per_batch, nt - t0);
-    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[0], st));
-    DW_TRY(forward(c, vol, 0, X, Y, Z, c->metas_dev + (size_t)t0 * M, tb * M, st));
-    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[1], st));
+    const int l = bi % nl;
+    Lane& ln = c->lanes[l];
+    if (ln.agg_pending) CU_TRY(cudaStreamWaitEvent(ln.stream_aux, ln.agg_done, 0));     // previous probs of this lane consumed
+    activate_lane(c, l);
+    const bool split = !c->stage_timing && c->split_streams;
+    cudaStream_t s_tc = split ? ln.stream : ln.stream_aux, s_last = ln.stream_aux;
+    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[0], ln.stream_aux));
+    DW_TRY(forward(c, vol, 0, X, Y, Z, c->metas_dev + (size_t)t0 * M, tb * M, s_tc, ln.stream_aux, &ln, &s_last));
+    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[1], s_last));
+    CU_TRY(cudaEventRecord(ln.fwd_done, s_last));
+    CU_TRY(cudaStreamWaitEvent(st, ln.fwd_done, 0));
+    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[3], st));
     for (int t = 0; t < tb; ++t) {
       aggregate_tile_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
-          c->probs + (size_t)t * M * 2 * P, c->metas_dev + (size_t)(t0 + t) * M, M, gauss ? c->gauss_dev : nullptr,
+          ln.probs + (size_t)t * M * 2 * P, c->metas_dev + (size_t)(t0 + t) * M, M, gauss ? c->gauss_dev : nullptr,
           agg, wgt, ps[0], ps[1], ps[2], X, Y, Z);
       c->launches++;
     }
+    CU_TRY(cudaEventRecord(ln.agg_done, st));
+    ln.agg_pending = true;
     if (c->stage_timing) {
       CU_TRY(cudaEventRecord(c->ev[2], st));
       CU_TRY(cudaEventSynchronize(c->ev[2]));
       float a = 0, b = 0;
-      cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
+      cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); cudaEventElapsedTime(&b, c->ev[3], c->ev[2]);
       conv_ms += a; agg_ms += b;
       for (int i = 0; i + 1 < c->tcev_used; i += 2) { float t = 0; cudaEventElapsedTime(&t, c->tcev[i], c->tcev[i + 1]); c->tc_ms += t; }
       c->tcev_used = 0;

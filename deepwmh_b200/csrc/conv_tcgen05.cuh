@@ -462,6 +462,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 // ------------------------------------------------------------------------------------------------
 struct TcLayer {
   bool enabled = false;
+  int ms0[6] = {0, 0, 0, 0, 0, 0}, ms1[6] = {0, 0, 0, 0, 0, 0};   // tensor-map specs {n, C, D, H, W, KC}; ms1[0] == 0 -> no second input
+  bool map_bf16 = false;
   CUtensorMap tm0, tm1;
   void* wpack = nullptr;
   TcKParams kp{};
@@ -502,6 +504,14 @@ inline bool tc_make_map(CUtensorMap* m, const void* base, int maxN, int C, int D
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { *why = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r); return false; }
   return true;
+}
+
+// (re)encode the input tensor maps of a prepared layer for another set of activation buffers
+inline int tc_remap(TcLayer& t, const void* in0, const void* in1, std::string* why) {
+  if (!tc_make_map(&t.tm0, in0, t.ms0[0], t.ms0[1], t.ms0[2], t.ms0[3], t.ms0[4], t.ms0[5], t.map_bf16, why)) return 1;
+  if (t.ms1[0] > 0) { if (!tc_make_map(&t.tm1, in1, t.ms1[0], t.ms1[1], t.ms1[2], t.ms1[3], t.ms1[4], t.ms1[5], t.map_bf16, why)) return 1; }
+  else t.tm1 = t.tm0;
+  return 0;
 }
 
 inline uint16_t tc_to_bits(float v, bool bf16) {
@@ -632,9 +642,10 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   if (cudaMemcpy(t.wpack, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy(wpack) failed"; return 1; }
   kp.wpack = t.wpack;
   // input maps: the (possibly parity-split) producer tensor has nclass * C0 channels at the reduced resolution
-  if (!tc_make_map(&t.tm0, in0, maxN * kp.nclass, c0, in_sp[0] / sd, in_sp[1] / sh, in_sp[2] / sw, KC, bf16, why)) return 1;
-  if (c1 > 0) { if (!tc_make_map(&t.tm1, in1, maxN, c1, in_sp[0], in_sp[1], in_sp[2], KC, bf16, why)) return 1; }
-  else t.tm1 = t.tm0;
+  t.map_bf16 = bf16;
+  { const int a0[6] = {maxN * kp.nclass, c0, in_sp[0] / sd, in_sp[1] / sh, in_sp[2] / sw, KC}; for (int i = 0; i < 6; ++i) t.ms0[i] = a0[i]; }
+  { const int a1[6] = {c1 > 0 ? maxN : 0, c1, in_sp[0], in_sp[1], in_sp[2], KC}; for (int i = 0; i < 6; ++i) t.ms1[i] = a1[i]; }
+  if (tc_remap(t, in0, in1, why)) return 1;
   t.enabled = true;
   return 0;
 }
@@ -696,8 +707,10 @@ inline int tc_prepare_tconv(TcLayer& t, const std::vector<float>& w, int cin, in
   if (cudaMalloc(&t.wpack, pk.size() * 2) != cudaSuccess) { *why = "cudaMalloc(wpack) failed"; return 1; }
   if (cudaMemcpy(t.wpack, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy(wpack) failed"; return 1; }
   kp.wpack = t.wpack;
-  if (!tc_make_map(&t.tm0, in0, maxN, cin, in_sp[0], in_sp[1], in_sp[2], KC, bf16, why)) return 1;
-  t.tm1 = t.tm0;
+  t.map_bf16 = bf16;
+  { const int a0[6] = {maxN, cin, in_sp[0], in_sp[1], in_sp[2], KC}; for (int i = 0; i < 6; ++i) t.ms0[i] = a0[i]; }
+  t.ms1[0] = 0;
+  if (tc_remap(t, in0, nullptr, why)) return 1;
   t.enabled = true;
   return 0;
 }

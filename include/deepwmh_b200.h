@@ -40,7 +40,9 @@ typedef struct dwmh_net_desc {
   int32_t pool_op_kernel_sizes[DWMH_MAX_POOL][3];      /* each entry 1 or 2                          */
   int32_t conv_kernel_sizes[DWMH_MAX_POOL + 1][3];     /* each entry 1 or 3                          */
   int32_t act_dtype;                          /* 0 = fp16 operands/storage (default), 1 = bf16       */
-  int32_t max_batch;                          /* patch forwards kept in flight (multiple of 8), 0 = default */
+  int32_t max_batch;                          /* patch forwards per lane batch (multiple of 8), 0 = default 8 */
+  int32_t lanes;                              /* independent forward pipelines on separate streams, 0 = default 1
+                                               * (measured on B200: kernels of different lanes do not co-run, so >1 buys nothing yet) */
 } dwmh_net_desc;
 
 const char* dwmh_last_error(void);

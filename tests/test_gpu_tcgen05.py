@@ -14,13 +14,13 @@ from conftest import small_plans
 
 
 def test_sass_has_blackwell_native_instructions():
-    """CPU: cuobjdump of the in-tree library shows UTCHMMA (tcgen05.mma), UTMALDG (TMA), LDTM/STTM (TMEM)."""
+    """CPU: cuobjdump of the in-tree library shows UTCHMMA (tcgen05.mma), UTMALDG / UBLKCP (TMA), LDTM (TMEM load), UTCBAR (tcgen05.commit)."""
     from deepwmh_b200 import build as b
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", b.build()], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM", "UBLKCP"):
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP", "UTCBAR"):
         assert mnemonic in sass, mnemonic
 
 
