@@ -588,7 +588,10 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
       p.kd = L.k[0]; p.kh = L.k[1]; p.kw = L.k[2]; p.Cout = L.cout;
       dim3 grid((unsigned)((L.vout() + 256 * FC_VPT - 1) / (256 * FC_VPT)), nb);
       const size_t smem = ((size_t)taps * L.cout + 2 * L.cout) * sizeof(float);
-      if (taps == 27) conv_first_kernel<T, true><<<grid, 256, smem, st>>>(p);
+      if (taps == 27 && L.cout <= 32 && L.out_sp[2] % 2 == 0) {
+        dim3 grid2((unsigned)((L.vout() / 2 + 128 * FC_VPT - 1) / (128 * FC_VPT)), nb);
+        conv_first_k3x2_kernel<T><<<grid2, 128, smem, st>>>(p);
+      } else if (taps == 27) conv_first_kernel<T, true><<<grid, 256, smem, st>>>(p);
       else conv_first_kernel<T, false><<<grid, 256, smem, st>>>(p);
       c->launches++;
     } else if (L.kind == L_CONV) {

@@ -34,13 +34,14 @@
 
 namespace dwmh {
 
-constexpr int TC_THREADS = 224;
+constexpr int TC_WARPS_PER_GROUP = 7;
+constexpr int TC_THREADS = 224;          // per group; a dual-group CTA has 448
 constexpr int TC_TH = 16, TC_TW = 8;
 constexpr int TC_PH = 18, TC_PW = 10;
 constexpr int TC_PLANE_BYTES = TC_PH * TC_PW * 16;     // one 8-channel chunk of a haloed plane
 constexpr int TC_MAX_SA = 4, TC_MAX_NB = 40, TC_MAX_R = 16;
 constexpr int TC_SMEM_MAX = 232448;                    // 227 KB opt-in limit
-constexpr int TC_SMEM_RESERVED = 3072;                 // barriers + TMEM pointer + statistics
+constexpr int TC_SMEM_RESERVED = 5120;                 // barriers + TMEM pointer + statistics
 
 // One parity class of a strided conv (a plain stride-1 conv has exactly one class).  The producer tensor of
 // a strided conv is stored a second time parity-split ("space to depth": [n][class][C/8][D/sd][H/sh][W/sw][8]),
@@ -57,6 +58,8 @@ struct TcKParams {
   TcClassDesc cls[8];
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
   int SA, NB, resident, R, fmt;
+  int G;              // work-item pipelines ("groups") per CTA: 2 = two tiles share the resident weights, each with 256 TMEM columns
+  int total_items;
   unsigned long long* prof;   // dbg & 8: per-role wait/total cycle counters
   int dbg;            // profiling knobs (env DWMH_TC_DEBUG): 1 = no activation TMA, 2 = no MMA, 4 = no epilogue stores
   uint32_t a_stage_bytes, b_tile_bytes, off_b, off_bar;
@@ -66,6 +69,7 @@ struct TcKParams {
 struct RingPos {
   uint32_t idx = 0, phase = 0;
   __device__ __forceinline__ void advance(uint32_t n) { if (++idx == n) { idx = 0; phase ^= 1; } }
+  __device__ __forceinline__ RingPos next(uint32_t n) const { RingPos r = *this; r.advance(n); return r; }
 };
 
 #define DWMH_TIMED_WAIT(acc, ...) do { if (prof_on) { const long long t__ = clock64(); __VA_ARGS__; acc += clock64() - t__; } else { __VA_ARGS__; } } while (0)
@@ -73,14 +77,21 @@ struct RingPos {
 __device__ __forceinline__ uint64_t tc_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
 // KSTEPS = KC/16 (UMMA K steps per channel chunk); SMALL_CB: CB <= 32 -> per-thread running statistics.
-template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV, bool DUAL>
+__global__ void __launch_bounds__(DUAL ? 2 * TC_THREADS : TC_THREADS, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const TcKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = tc::smem_u32(smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_abs = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Dual-group CTA: two independent tile pipelines (own activation ring, accumulator ring, warps) share the
+  // resident weight tiles; while one group's issue thread sits in barrier latency or bookkeeping the other
+  // group's MMAs keep the tensor pipe busy.
+  const int g = warp_abs / TC_WARPS_PER_GROUP;
+  const int warp = warp_abs - g * TC_WARPS_PER_GROUP;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer
 
-  int wi = blockIdx.x;
+  int wi = blockIdx.x * p.G + g;
+  const bool idle = wi >= p.total_items;
+  if (idle) wi = p.total_items - 1;
   const int tw = wi % p.tilesW; wi /= p.tilesW;
   const int th = wi % p.tilesH; wi /= p.tilesH;
   const int zb = wi % p.nzb; wi /= p.nzb;
@@ -90,31 +101,39 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int z_lo = zb * p.ZB, z_end = min(p.D, z_lo + p.ZB);
   const uint32_t SA = p.SA, NB = p.NB, R = p.R, CB = p.CB;
 
-  const uint32_t bar = smem_base + p.off_bar;
-  const uint32_t a_full = bar, a_empty = bar + 8u * SA, b_full = bar + 16u * SA, b_empty = b_full + 8u * NB;
-  const uint32_t acc_full = b_empty + 8u * NB, acc_empty = acc_full + 8u * R;
   const uint32_t nbar = 2 * SA + 2 * NB + 2 * R;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * nbar);
-  float* s_stat = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar + 16);       // [2][CB]
+  const uint32_t bar0 = smem_base + p.off_bar, bar = bar0 + (uint32_t)g * nbar * 8u;
+  const uint32_t a_full = bar, a_empty = bar + 8u * SA;
+  const uint32_t b_full = bar0 + 16u * SA, b_empty = b_full + 8u * NB;             // weight ring: shared, lives in group 0's block
+  const uint32_t acc_full = bar + 16u * SA + 16u * NB, acc_empty = acc_full + 8u * R;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * nbar * p.G);
+  float* s_stat = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)g * 2 * CB;   // [2][CB] per group
+  const uint32_t smem_a = smem_base + (uint32_t)g * SA * p.a_stage_bytes;          // this group's activation ring
 
   if (threadIdx.x == 0) {
     tc::prefetch_tensormap(&tmA0);
     tc::prefetch_tensormap(&tmA1);
-    for (uint32_t s = 0; s < SA; ++s) { tc::mbar_init(a_full + 8 * s, 1); tc::mbar_init(a_empty + 8 * s, 1); }
-    for (uint32_t s = 0; s < NB; ++s) { tc::mbar_init(b_full + 8 * s, 1); tc::mbar_init(b_empty + 8 * s, 1); }
-    for (uint32_t s = 0; s < R; ++s) { tc::mbar_init(acc_full + 8 * s, 1); tc::mbar_init(acc_empty + 8 * s, 4); }
+    for (int gg = 0; gg < p.G; ++gg) {
+      const uint32_t bg = bar0 + (uint32_t)gg * nbar * 8u;
+      for (uint32_t s_ = 0; s_ < SA; ++s_) { tc::mbar_init(bg + 8 * s_, 1); tc::mbar_init(bg + 8 * (SA + s_), 1); }
+      for (uint32_t s_ = 0; s_ < R; ++s_) { tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * s_, 1); tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * (R + s_), 4); }
+    }
+    for (uint32_t s_ = 0; s_ < NB; ++s_) { tc::mbar_init(b_full + 8 * s_, 1); tc::mbar_init(b_empty + 8 * s_, 1); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc(tc::smem_u32(tmem_ptr_smem), 512);
-  if constexpr (!TCONV) for (int i = threadIdx.x; i < 2 * (int)CB; i += TC_THREADS) s_stat[i] = 0.f;
+  if (warp_abs == 1) tc::tmem_alloc(tc::smem_u32(tmem_ptr_smem), 512);
+  if constexpr (!TCONV) for (int i = threadIdx.x; i < 2 * (int)CB * p.G; i += blockDim.x) (s_stat - (size_t)g * 2 * CB)[i] = 0.f;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem = *tmem_ptr_smem;
+  const uint32_t tmem = *tmem_ptr_smem + (uint32_t)g * 256u;       // group 1 owns TMEM columns 256..511
   const bool prof_on = (p.dbg & 8) != 0;
   long long w0_ = 0, w1_ = 0;
   const long long tstart_ = clock64();
 
+  if (idle) {
+    // odd item count: the second group of the last CTA has nothing to do
+  } else
   if (warp == 0) {
     // ---------------- activation producer: one TMA box per (input plane, channel chunk) -----------
     const bool leader = tc::elect_one();
@@ -130,7 +149,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             tc::mbar_arrive_expect_tx(a_full + 8 * a.idx, p.a_stage_bytes);
             const bool first = kc < p.nkc0;
             const int c8 = first ? (n * p.nclass + c) * (p.C0 >> 3) + kc * (2 * KSTEPS) : n * (p.C1 >> 3) + (kc - p.nkc0) * (2 * KSTEPS);
-            tc::tma_load_4d(smem_base + a.idx * p.a_stage_bytes, first ? &tmA0 : &tmA1, a_full + 8 * a.idx, (w0 - 1) * 8, h0 - 1, t, c8);
+            tc::tma_load_4d(smem_a + a.idx * p.a_stage_bytes, first ? &tmA0 : &tmA1, a_full + 8 * a.idx, (w0 - 1) * 8, h0 - 1, t, c8);
           }
           a.advance(SA);
         }
@@ -142,7 +161,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int ntile = p.nkc * p.tiles_per_kc;
     const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)cb * ntile * p.b_tile_bytes;
     if (p.resident) {
-      if (leader)
+      if (leader && g == 0)
         for (int t = 0; t < ntile; ++t) {
           tc::mbar_arrive_expect_tx(b_full + 8 * t, p.b_tile_bytes);
           tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
@@ -188,6 +207,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     if (p.resident)
       for (int t = 0; t < p.nkc * p.tiles_per_kc; ++t) tc::mbar_wait(b_full + 8 * t, 0, 5);
     RingPos a, b, fresh, done;
+    bool b_peek = false;      // same for the weight ring
+    bool a_peek = false;      // a_full of the CURRENT stage already observed complete (prefetched try_wait)
     uint32_t lo_slot = 0;
     int next_fresh = z_lo, next_done = z_lo, zo_lo_prev = z_lo;
     for (int t = t_first; t <= t_last_nominal; ++t) {
@@ -205,10 +226,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t col = tmem + lo_slot * CB;
         const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17), id3 = idesc0 | (((3 * CB) >> 3) << 17);
         for (int kc = 0; kc < p.nkc; ++kc) {
-          DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
+          if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
           tc::tc_fence_after();
+          { const RingPos an = a.next(SA); a_peek = tc::mbar_try_wait(a_full + 8 * an.idx, an.phase); }   // result consumed after the burst
           if (leader) {
-            const uint32_t a_lo0 = ((smem_base + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
 #pragma unroll
             for (int sft = 0; sft < 9; ++sft) {
@@ -257,20 +279,22 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
         const int tapmask = p.cls[c].tapmask;
         for (int kc = 0; kc < p.nkc; ++kc) {
-          DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
+          if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
+          a_peek = false;
           tc::tc_fence_after();
-          const uint32_t a_lo0 = ((smem_base + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
-          uint32_t tile = (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0);
-          for (int m = tapmask; m; m &= m - 1, ++tile) {
+          const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+          uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0) * tile16;
+          for (int m = tapmask; m; m &= m - 1) {
             const int sft = __ffs(m) - 1;
             uint32_t b_lo0;
-            if (p.resident) b_lo0 = b_lo_res + tile * tile16;
+            if (p.resident) { b_lo0 = b_res; b_res += tile16; }
             else {
-              DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
+              if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
               tc::tc_fence_after();
               b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+              { const RingPos bn = b.next(NB); b_peek = tc::mbar_try_wait(b_full + 8 * bn.idx, bn.phase); }   // consumed at the next tap
             }
-            const uint32_t a_lo1 = a_lo0 + (uint32_t)(sft / 3) * TC_PW + (uint32_t)(sft % 3);
+            const uint32_t a_lo1 = a_lo0 + (uint32_t)((sft / 3) * TC_PW + (sft % 3));
             if (first_mma) {
               // first MMA of the step: slot by slot, overwriting (accumulate = 0) first-touched slots
               for (uint32_t i = 0; i < cnt; ++i) {
@@ -310,7 +334,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
   } else {
     // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ---------------------------
-    const int q = warp & 3;
+    const int q = warp_abs & 3;       // TMEM lane quarter is fixed by the hardware warp id
     const int row = q * 32 + lane;
     const int h = h0 + (row >> 3), w = w0 + (row & 7);
     const bool valid = h < p.H && w < p.W && !(p.dbg & 4);
@@ -440,7 +464,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
     }   // !TCONV
   }
-  if (prof_on && lane == 0 && (warp <= 2 || warp == 6)) {
+  if (prof_on && lane == 0 && g == 0 && (warp <= 2 || warp == 6)) {
     const int role = warp == 6 ? 3 : warp;          // 0 act producer, 1 mma, 2 epilogue (warp 2), 3 weight producer
     atomicAdd(p.prof + role * 4 + 0, (unsigned long long)w0_);
     atomicAdd(p.prof + role * 4 + 1, (unsigned long long)w1_);
@@ -449,12 +473,13 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   tc::tc_fence_before();
   __syncthreads();
   if constexpr (!TCONV) {
-    for (int i = threadIdx.x; i < 2 * (int)CB; i += TC_THREADS) {
-      const int c = i % (int)CB, which = i / (int)CB;
-      atomicAdd(p.sums + ((size_t)n * p.Cout + (size_t)cb * CB + c) * 2 + which, (double)s_stat[i]);
-    }
+    if (!idle)
+      for (int i = threadIdx.x - g * TC_THREADS; i < 2 * (int)CB; i += TC_THREADS) {      // each group flushes its own tile's sums
+        const int c = i % (int)CB, which = i / (int)CB;
+        atomicAdd(p.sums + ((size_t)n * p.Cout + (size_t)cb * CB + c) * 2 + which, (double)s_stat[i]);
+      }
   }
-  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+  if (warp_abs == 1) tc::tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,21 +599,36 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
       }
   kp.tiles_per_kc = tile0;
   // ---- tiling / shared-memory plan ----
-  int KC = 64;
-  while (KC > 16 && (c0 % KC || c1 % KC)) KC >>= 1;
+  int KC0 = 64;
+  while (KC0 > 16 && (c0 % KC0 || c1 % KC0)) KC0 >>= 1;
   const int budget = TC_SMEM_MAX - TC_SMEM_RESERVED;
-  int CB = 0, SA = 0, NB = 0, resident = 0;
-  for (;;) {
-    const int a_stage = KC * 360;
-    const int nkc = cin / KC;
-    const int ntile = nkc * kp.tiles_per_kc;
+  int KC = 0, CB = 0, SA = 0, NB = 0, resident = 0, G = 1;
+  static int allow_dual = -1;
+  if (allow_dual < 0) { const char* e = getenv("DWMH_TC_DUAL"); allow_dual = e ? atoi(e) : 1; }
+  // (1) dual-group resident plan: two tile pipelines share the resident weights (each gets 256 TMEM columns)
+  for (int kc = KC0; kc >= 16 && !CB && allow_dual; kc >>= 1) {
+    const int a_stage = kc * 360, ntile = (cin / kc) * kp.tiles_per_kc;
+    if (ntile > TC_MAX_NB) continue;
+    for (int cbt = std::min(cout, 64); cbt >= 32; cbt -= 16) {
+      if (cout % cbt) continue;
+      const long long btot = (long long)ntile * kp.jmax * cbt * kc * 2;
+      if (btot + 2LL * 3 * a_stage <= budget) {
+        KC = kc; CB = cbt; resident = 1; NB = ntile; G = 2;
+        SA = (int)std::min<long long>(TC_MAX_SA, (budget - btot) / (2LL * a_stage));
+        break;
+      }
+    }
+  }
+  // (2) single-group plans
+  for (int kc = KC0; kc >= 16 && !CB; kc >>= 1) {
+    const int a_stage = kc * 360, ntile = (cin / kc) * kp.tiles_per_kc;
     if (ntile <= TC_MAX_NB) {
       for (int cbt = std::min(cout, 128); cbt >= 16; cbt -= 16) {
         if (cout % cbt) continue;
         if (cbt < 32 && cbt != cout) break;
-        const long long btot = (long long)ntile * kp.jmax * cbt * KC * 2;
+        const long long btot = (long long)ntile * kp.jmax * cbt * kc * 2;
         if (btot + 2LL * a_stage <= budget) {
-          CB = cbt; resident = 1; NB = ntile;
+          KC = kc; CB = cbt; resident = 1; NB = ntile;
           SA = (int)std::min<long long>(TC_MAX_SA, (budget - btot) / a_stage);
           break;
         }
@@ -597,23 +637,21 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
     if (!CB) {      // streaming weights
       for (int cbt = std::min(cout, 128); cbt >= 16; cbt -= 16) {
         if (cout % cbt) continue;
-        const int b_tile = kp.jmax * cbt * KC * 2;
+        const int b_tile = kp.jmax * cbt * kc * 2;
         const int nb = (budget - 3 * a_stage) / b_tile;
-        if (nb >= 3) { CB = cbt; resident = 0; SA = 3; NB = std::min(nb, TC_MAX_NB); break; }
+        if (nb >= 3) { KC = kc; CB = cbt; resident = 0; SA = 3; NB = std::min(nb, TC_MAX_NB); break; }
       }
     }
-    if (CB || KC == 16) break;
-    KC >>= 1;
   }
   if (!CB) return 0;
   kp.C0 = c0; kp.C1 = c1; kp.Cout = cout; kp.CB = CB; kp.KC = KC; kp.nkc = cin / KC; kp.nkc0 = c0 / KC;
   kp.D = out_sp[0]; kp.H = out_sp[1]; kp.W = out_sp[2];
   kp.tilesH = (kp.H + TC_TH - 1) / TC_TH; kp.tilesW = (kp.W + TC_TW - 1) / TC_TW;
-  kp.ncb = cout / CB; kp.SA = SA; kp.NB = NB; kp.resident = resident;
-  kp.R = std::min(TC_MAX_R, 512 / CB);
+  kp.ncb = cout / CB; kp.SA = SA; kp.NB = NB; kp.resident = resident; kp.G = G;
+  kp.R = std::min(TC_MAX_R, (512 / G) / CB);
   kp.fmt = bf16 ? 1 : 0;
   kp.a_stage_bytes = KC * 360; kp.b_tile_bytes = kp.jmax * CB * KC * 2;
-  kp.off_b = SA * kp.a_stage_bytes;
+  kp.off_b = G * SA * kp.a_stage_bytes;
   kp.off_bar = kp.off_b + NB * kp.b_tile_bytes;
   kp.off_bar = (kp.off_bar + 127) & ~127u;
   t.smem_bytes = kp.off_bar + TC_SMEM_RESERVED;
@@ -682,7 +720,7 @@ inline int tc_prepare_tconv(TcLayer& t, const std::vector<float>& w, int cin, in
   kp.D = in_sp[0]; kp.H = in_sp[1]; kp.W = in_sp[2];
   kp.tilesH = (kp.H + TC_TH - 1) / TC_TH; kp.tilesW = (kp.W + TC_TW - 1) / TC_TW;
   kp.ncb = cout / CBt; kp.SA = SA; kp.NB = NB; kp.resident = resident;
-  kp.R = 512 / CB; kp.fmt = bf16 ? 1 : 0;
+  kp.R = 512 / CB; kp.fmt = bf16 ? 1 : 0; kp.G = 1;
   kp.a_stage_bytes = a_stage; kp.b_tile_bytes = b_tile;
   kp.off_b = SA * a_stage;
   kp.off_bar = (kp.off_b + NB * b_tile + 127) & ~127u;
@@ -718,10 +756,12 @@ inline int tc_prepare_tconv(TcLayer& t, const std::vector<float>& w, int cin, in
 template <typename T>
 inline int tc_set_attr_all() {
   cudaError_t e = cudaSuccess;
-#define DWMH_TC_ATTR(K, S, C) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, K, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)
-  DWMH_TC_ATTR(1, true, false); DWMH_TC_ATTR(2, true, false); DWMH_TC_ATTR(4, true, false);
-  DWMH_TC_ATTR(1, false, false); DWMH_TC_ATTR(2, false, false); DWMH_TC_ATTR(4, false, false);
-  DWMH_TC_ATTR(1, false, true); DWMH_TC_ATTR(2, false, true); DWMH_TC_ATTR(4, false, true);
+#define DWMH_TC_ATTR(K, S, C, D) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, K, S, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)
+  DWMH_TC_ATTR(1, true, false, false); DWMH_TC_ATTR(2, true, false, false); DWMH_TC_ATTR(4, true, false, false);
+  DWMH_TC_ATTR(1, false, false, false); DWMH_TC_ATTR(2, false, false, false); DWMH_TC_ATTR(4, false, false, false);
+  DWMH_TC_ATTR(1, false, true, false); DWMH_TC_ATTR(2, false, true, false); DWMH_TC_ATTR(4, false, true, false);
+  DWMH_TC_ATTR(1, true, false, true); DWMH_TC_ATTR(2, true, false, true); DWMH_TC_ATTR(4, true, false, true);
+  DWMH_TC_ATTR(1, false, false, true); DWMH_TC_ATTR(2, false, false, true); DWMH_TC_ATTR(4, false, false, true);
 #undef DWMH_TC_ATTR
   return e == cudaSuccess ? 0 : 1;
 }
@@ -737,7 +777,13 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 2) ZB = (ZB + 1) / 2;
   kp.ZB = ZB; kp.nzb = (kp.D + ZB - 1) / ZB;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DWMH_TC_DEBUG"); dbg = e ? atoi(e) : 0; } kp.dbg = dbg; }
-  const unsigned grid = (unsigned)((long long)nb * kp.ncb * kp.nzb * tiles);
+  const long long items = (long long)nb * kp.ncb * kp.nzb * tiles;
+  // both groups of a CTA must share the cout block whose weights are resident: pairs (2k, 2k+1) stay inside
+  // one (n, cb) when the tiles x z-blocks count is even
+  if (kp.G == 2 && ((long long)kp.nzb * tiles) % 2 != 0) kp.G = 1;
+  kp.total_items = (int)items;
+  const unsigned grid = (unsigned)((items + kp.G - 1) / kp.G);
+  const unsigned threads = TC_THREADS * kp.G;
   static unsigned long long* prof_dev = nullptr;
   if (kp.dbg & 8) {
     if (!prof_dev) cudaMalloc((void**)&prof_dev, 16 * sizeof(unsigned long long));
@@ -746,10 +792,12 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   kp.prof = prof_dev;
   const int ks = kp.KC / 16;
   const bool small = kp.CB <= 32 && !kp.tconv;
-#define DWMH_TC_LAUNCH(K, S, C) conv3_tc_kernel<T, K, S, C><<<grid, TC_THREADS, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
-  if (kp.tconv) { if (ks == 1) DWMH_TC_LAUNCH(1, false, true); else if (ks == 2) DWMH_TC_LAUNCH(2, false, true); else DWMH_TC_LAUNCH(4, false, true); }
-  else if (small) { if (ks == 1) DWMH_TC_LAUNCH(1, true, false); else if (ks == 2) DWMH_TC_LAUNCH(2, true, false); else DWMH_TC_LAUNCH(4, true, false); }
-  else { if (ks == 1) DWMH_TC_LAUNCH(1, false, false); else if (ks == 2) DWMH_TC_LAUNCH(2, false, false); else DWMH_TC_LAUNCH(4, false, false); }
+#define DWMH_TC_LAUNCH(K, S, C, D) conv3_tc_kernel<T, K, S, C, D><<<grid, threads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
+#define DWMH_TC_LAUNCH_K(S, C, D) do { if (ks == 1) DWMH_TC_LAUNCH(1, S, C, D); else if (ks == 2) DWMH_TC_LAUNCH(2, S, C, D); else DWMH_TC_LAUNCH(4, S, C, D); } while (0)
+  if (kp.tconv) DWMH_TC_LAUNCH_K(false, true, false);
+  else if (kp.G == 2) { if (small) DWMH_TC_LAUNCH_K(true, false, true); else DWMH_TC_LAUNCH_K(false, false, true); }
+  else { if (small) DWMH_TC_LAUNCH_K(true, false, false); else DWMH_TC_LAUNCH_K(false, false, false); }
+#undef DWMH_TC_LAUNCH_K
 #undef DWMH_TC_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv3_tc_kernel launch failed: ") + cudaGetErrorString(e); return 1; }

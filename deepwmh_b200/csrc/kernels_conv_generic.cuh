@@ -138,6 +138,99 @@ __global__ void __launch_bounds__(256) conv_first_kernel(FirstConvParams p) {
     atomicAdd(p.sums + (size_t)n * p.Cout * 2 + c, (double)sstat[c]);
 }
 
+// 3x3x3 specialisation with TWO z-adjacent voxels per thread: one broadcast weight load feeds 16 FMAs
+// (the one-voxel form is bound by the shared-memory port: 1 LDS.128 per 4 FMAs), and the pair shares its
+// 3x3x4 input neighbourhood.  Requires pz even and Cout <= 32.
+template <typename T>
+__global__ void __launch_bounds__(128) conv_first_k3x2_kernel(FirstConvParams p) {
+  extern __shared__ float smf[];                 // weights [27][Cout], then stats [Cout][2]
+  float* sw = smf;
+  float* sstat = smf + 27 * p.Cout;
+  for (int i = threadIdx.x; i < 27 * p.Cout; i += blockDim.x) sw[i] = p.w[i];
+  for (int i = threadIdx.x; i < 2 * p.Cout; i += blockDim.x) sstat[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int64_t P = (int64_t)p.px * p.py * p.pz, P2 = P >> 1;
+  int ox = 0, oy = 0, oz = 0, flip = 0;
+  const float* src = p.src;
+  int SY = p.SY, SZ = p.SZ;
+  if (p.patch_mode) { src += (size_t)n * P; SY = p.py; SZ = p.pz; }
+  else { const SampleMeta m = p.metas[n]; ox = m.ox; oy = m.oy; oz = m.oz; flip = m.flip; }
+  const int lane = threadIdx.x & 31;
+  const int pz2 = p.pz >> 1;
+  float rs[32], rq[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) { rs[q] = 0.f; rq[q] = 0.f; }
+  for (int it = 0; it < FC_VPT; ++it) {
+    const int64_t v2 = ((int64_t)blockIdx.x * FC_VPT + it) * blockDim.x + threadIdx.x;      // voxel-pair index
+    const bool active = v2 < P2;
+    const int k = (int)(v2 % pz2) * 2, j = (int)((v2 / pz2) % p.py), i = (int)(v2 / ((int64_t)pz2 * p.py));
+    float xin[9][4];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int ii = i + a - 1, jj = j + b - 1, kk = k + c - 1;
+          float val = 0.f;
+          if (active && ii >= 0 && ii < p.px && jj >= 0 && jj < p.py && kk >= 0 && kk < p.pz) {
+            const int si = ox + ((flip & 4) ? p.px - 1 - ii : ii);
+            const int sj = oy + ((flip & 2) ? p.py - 1 - jj : jj);
+            const int sk = oz + ((flip & 1) ? p.pz - 1 - kk : kk);
+            val = __ldg(src + ((size_t)si * SY + sj) * SZ + sk);
+          }
+          xin[a * 3 + b][c] = val;
+        }
+    const int64_t v = ((int64_t)i * p.py + j) * p.pz + k;
+    uint4* outp = reinterpret_cast<uint4*>(p.out) + (size_t)n * (p.Cout >> 3) * P + v;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      if (cc < (p.Cout >> 3)) {
+        float a0[8], a1[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { a0[q] = 0.f; a1[q] = 0.f; }
+#pragma unroll
+        for (int ab = 0; ab < 9; ++ab)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + (ab * 3 + c) * p.Cout + cc * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + (ab * 3 + c) * p.Cout + cc * 8 + 4);
+            const float x0 = xin[ab][c], x1 = xin[ab][c + 1];
+            a0[0] = fmaf(x0, w0.x, a0[0]); a0[1] = fmaf(x0, w0.y, a0[1]); a0[2] = fmaf(x0, w0.z, a0[2]); a0[3] = fmaf(x0, w0.w, a0[3]);
+            a0[4] = fmaf(x0, w1.x, a0[4]); a0[5] = fmaf(x0, w1.y, a0[5]); a0[6] = fmaf(x0, w1.z, a0[6]); a0[7] = fmaf(x0, w1.w, a0[7]);
+            a1[0] = fmaf(x1, w0.x, a1[0]); a1[1] = fmaf(x1, w0.y, a1[1]); a1[2] = fmaf(x1, w0.z, a1[2]); a1[3] = fmaf(x1, w0.w, a1[3]);
+            a1[4] = fmaf(x1, w1.x, a1[4]); a1[5] = fmaf(x1, w1.y, a1[5]); a1[6] = fmaf(x1, w1.z, a1[6]); a1[7] = fmaf(x1, w1.w, a1[7]);
+          }
+        if (active) {
+          outp[(size_t)cc * P] = pack8<T>(a0);
+          outp[(size_t)cc * P + 1] = pack8<T>(a1);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            rs[cc * 8 + q] += a0[q] + a1[q];
+            rq[cc * 8 + q] = fmaf(a0[q], a0[q], fmaf(a1[q], a1[q], rq[cc * 8 + q]));
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 16; k >= 1; k >>= 1) {
+    const bool up = (lane & k) != 0;
+#pragma unroll
+    for (int i = 0; i < k; ++i) {
+      const float sa_ = up ? rs[i] : rs[i + k], ka_ = up ? rs[i + k] : rs[i];
+      const float sb_ = up ? rq[i] : rq[i + k], kb_ = up ? rq[i + k] : rq[i];
+      rs[i] = ka_ + __shfl_xor_sync(0xffffffffu, sa_, k);
+      rq[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, k);
+    }
+  }
+  if (lane < p.Cout) { atomicAdd(&sstat[lane * 2], rs[0]); atomicAdd(&sstat[lane * 2 + 1], rq[0]); }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * p.Cout; c += blockDim.x)
+    atomicAdd(p.sums + (size_t)n * p.Cout * 2 + c, (double)sstat[c]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Generic direct conv on the chunked layout.  Block = 128 threads -> output tile 2(d) x 8(h) x 16(w),
 // 32 output channels; thread = 2 w-adjacent voxels x 32 channels (64 fp32 accumulators).  Input
