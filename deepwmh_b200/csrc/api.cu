@@ -57,6 +57,7 @@ struct Layer {
   // device
   void* out = nullptr;              // [maxN][cout/8][V][8] T: normalised+activated (raw for the last conv / tconv)
   void* raw = nullptr;              // raw conv output; == out (normalised in place) unless raw32
+  bool fused_norm = false;          // no norm pass: the (single) consumer applies InstanceNorm+LeakyReLU on load
   bool raw32 = false;               // raw output kept in fp32 (low-resolution layers: one rounding less per layer)
   void* s2d = nullptr;              // parity-split copy for a strided tcgen05 consumer
   int s2d_s[3] = {1, 1, 1};
@@ -96,7 +97,7 @@ struct dwmh_ctx {
   std::vector<float> w_head; bool have_head = false; float* w_head_dev = nullptr;
   bool committed = false;
   bool force_generic = false;
-  int raw32_max_edge = 128;
+  int raw32_max_edge = 64;
   // workspaces
   double* stats_arena = nullptr; size_t stats_bytes = 0;   // views of the active lane
   float* probs = nullptr;            // [maxN][2][P]
@@ -408,6 +409,20 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
       b.tm0 = L.tc.tm0; b.tm1 = L.tc.tm1;
     }
   }
+  // norm-on-load fusion: producer P feeds exactly one consumer, a tcgen05 layer whose shape supports the in-kernel
+  // transform, and P's raw output is fp16 (the transform works in place on the landed TMA box)
+  {
+    static int allow = -1;
+    if (allow < 0) { const char* e = getenv("DWMH_FUSE_NORM"); allow = e ? atoi(e) : 1; }
+    std::vector<int> uses(nL, 0);
+    for (auto& L : c->layers) { if (L.in0 >= 0) uses[L.in0]++; if (L.in1 >= 0) uses[L.in1]++; }
+    for (auto& L : c->layers) L.fused_norm = false;
+    for (auto& L : c->layers) {
+      if (!allow || L.kind != L_CONV || !L.tc.enabled || !L.tc.xform_ok || L.in0 < 0) continue;
+      Layer& P = c->layers[L.in0];
+      if (P.has_norm && !P.raw32 && uses[L.in0] == 1 && P.s2d_s[0] * P.s2d_s[1] * P.s2d_s[2] == 1 && P.cout <= 64) P.fused_norm = true;
+    }
+  }
   c->active_lane = -1;
   if (!c->zs_acc) CU_TRY(cudaMalloc((void**)&c->zs_acc, 4 * sizeof(double)));
   if (!c->gauss_custom) {
@@ -601,7 +616,11 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
         st = st_tc;
         const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
         if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
-        DW_TRY(tc_launch<T>(L.tc, nb, L.sums, c->num_sms, st, &g_err));
+        {
+          Layer& P = c->layers[L.in0];
+          TcXform xf{P.sums, P.gamma_dev, P.beta_dev, 1.0f / (float)P.vout()};
+          DW_TRY(tc_launch<T>(L.tc, nb, L.sums, c->num_sms, st, &g_err, P.fused_norm ? &xf : nullptr));
+        }
         if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
         done = true; c->launches++;
       }
@@ -640,7 +659,7 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
       c->launches++;
     }
     c->conv_flops += L.flops_per_sample() * nb;
-    if (L.has_norm && (int)li != c->last_conv) {
+    if (L.has_norm && (int)li != c->last_conv && !(L.fused_norm && !c->force_generic)) {
       if (hop.to(st_aux)) return fail("stream hop failed");
       st = st_aux;
       NormParams np{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
@@ -703,7 +722,7 @@ extern "C" int dwmh_debug_layer_output(dwmh_ctx* c, int32_t li, float* out, int6
   CU_TRY(cudaSetDevice(c->device));
   // the last conv is kept raw (the head normalises on load): normalise here for a uniform view
   NormParams np{nullptr, nullptr, nullptr, 0.f};
-  if ((int)li == c->last_conv) np = NormParams{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
+  if ((int)li == c->last_conv || (L.fused_norm && !c->force_generic)) np = NormParams{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
   if (c->bf16) unpack_layer_kernel<__nv_bfloat16><<<c->num_sms * 4, 256, 0, st>>>((const __nv_bfloat16*)L.out, np, out, nn, L.cout, L.vout());
   else unpack_layer_kernel<__half><<<c->num_sms * 4, 256, 0, st>>>((const __half*)L.out, np, out, nn, L.cout, L.vout());
   CU_TRY(cudaGetLastError());

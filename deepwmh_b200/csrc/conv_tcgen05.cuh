@@ -58,6 +58,9 @@ struct TcKParams {
   TcClassDesc cls[8];
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
   int SA, NB, resident, R, fmt;
+  // norm-on-load (XFORM kernels): the input tensor is the producer's RAW fp16 output; InstanceNorm + LeakyReLU of the
+  // producer are applied to each landed plane in shared memory by the two producer warps before the MMA reads it
+  const double* xf_sums; const float* xf_gamma; const float* xf_beta; float xf_inv_count; int xform;
   int G;              // work-item pipelines ("groups") per CTA: 2 = two tiles share the resident weights, each with 256 TMEM columns
   int total_items;
   unsigned long long* prof;   // dbg & 8: per-role wait/total cycle counters
@@ -77,8 +80,8 @@ struct RingPos {
 __device__ __forceinline__ uint64_t tc_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
 // KSTEPS = KC/16 (UMMA K steps per channel chunk); SMALL_CB: CB <= 32 -> per-thread running statistics.
-template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV, bool DUAL>
-__global__ void __launch_bounds__(DUAL ? 2 * TC_THREADS : TC_THREADS, 1)
+template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV, bool DUAL, bool XFORM>
+__global__ void __launch_bounds__((DUAL ? 2 : 1) * (XFORM ? TC_THREADS + 64 : TC_THREADS), 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const TcKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = tc::smem_u32(smem);
@@ -86,8 +89,10 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   // Dual-group CTA: two independent tile pipelines (own activation ring, accumulator ring, warps) share the
   // resident weight tiles; while one group's issue thread sits in barrier latency or bookkeeping the other
   // group's MMAs keep the tensor pipe busy.
-  const int g = warp_abs / TC_WARPS_PER_GROUP;
-  const int warp = warp_abs - g * TC_WARPS_PER_GROUP;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer
+  constexpr int WPG = XFORM ? TC_WARPS_PER_GROUP + 2 : TC_WARPS_PER_GROUP;     // XFORM: two extra transform warps (7, 8)
+  constexpr int TPG = WPG * 32;
+  const int g = warp_abs / WPG;
+  const int warp = warp_abs - g * WPG;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer, 7..8 transform
 
   int wi = blockIdx.x * p.G + g;
   const bool idle = wi >= p.total_items;
@@ -101,13 +106,16 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const int z_lo = zb * p.ZB, z_end = min(p.D, z_lo + p.ZB);
   const uint32_t SA = p.SA, NB = p.NB, R = p.R, CB = p.CB;
 
-  const uint32_t nbar = 2 * SA + 2 * NB + 2 * R;
+  const uint32_t nbar = 3 * SA + 2 * NB + 2 * R;      // a_full, a_empty, b_full, b_empty, acc_full, acc_empty, a_ready
   const uint32_t bar0 = smem_base + p.off_bar, bar = bar0 + (uint32_t)g * nbar * 8u;
   const uint32_t a_full = bar, a_empty = bar + 8u * SA;
   const uint32_t b_full = bar0 + 16u * SA, b_empty = b_full + 8u * NB;             // weight ring: shared, lives in group 0's block
   const uint32_t acc_full = bar + 16u * SA + 16u * NB, acc_empty = acc_full + 8u * R;
+  const uint32_t a_ready = acc_empty + 8u * R;          // XFORM: plane transformed, ready for the MMA
+  const uint32_t a_mma = XFORM ? a_ready : a_full;      // what the MMA issuer waits on
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * nbar * p.G);
   float* s_stat = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)g * 2 * CB;   // [2][CB] per group
+  float* s_coef = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)g * 2 * 64;   // XFORM: a[64], b[64]
   const uint32_t smem_a = smem_base + (uint32_t)g * SA * p.a_stage_bytes;          // this group's activation ring
 
   if (threadIdx.x == 0) {
@@ -117,12 +125,22 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t bg = bar0 + (uint32_t)gg * nbar * 8u;
       for (uint32_t s_ = 0; s_ < SA; ++s_) { tc::mbar_init(bg + 8 * s_, 1); tc::mbar_init(bg + 8 * (SA + s_), 1); }
       for (uint32_t s_ = 0; s_ < R; ++s_) { tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * s_, 1); tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * (R + s_), 4); }
+      for (uint32_t s_ = 0; s_ < SA; ++s_) tc::mbar_init(bg + 16 * SA + 16 * NB + 16 * R + 8 * s_, 4);
     }
     for (uint32_t s_ = 0; s_ < NB; ++s_) { tc::mbar_init(b_full + 8 * s_, 1); tc::mbar_init(b_empty + 8 * s_, 1); }
     tc::fence_barrier_init();
   }
   if (warp_abs == 1) tc::tmem_alloc(tc::smem_u32(tmem_ptr_smem), 512);
   if constexpr (!TCONV) for (int i = threadIdx.x; i < 2 * (int)CB * p.G; i += blockDim.x) (s_stat - (size_t)g * 2 * CB)[i] = 0.f;
+  if constexpr (XFORM) {
+    const int tl = threadIdx.x - g * TPG;          // each group: coefficients of ITS sample
+    if (tl < p.C0 && !idle) {
+      NormParams np{p.xf_sums, p.xf_gamma, p.xf_beta, p.xf_inv_count};
+      float a_, b_;
+      norm_coeffs(np, n, p.C0, tl, a_, b_);
+      s_coef[tl] = a_; s_coef[64 + tl] = b_;
+    }
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -134,7 +152,70 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (idle) {
     // odd item count: the second group of the last CTA has nothing to do
   } else
-  if (warp == 0) {
+  if (XFORM && (warp == 0 || warp >= 6)) {
+    // ---------------- norm-on-load: warps 0, 6, 7, 8 transform every landed plane in place ----------
+    // (plain stride-1 layer with ONE 32-channel chunk per plane: each warp owns one 8-channel chunk, its 16
+    // coefficients live in registers.  Warp 0 also issues the TMA loads SA-2 planes ahead, so that waiting for a
+    // free slot never delays the transform of the plane the MMA needs next; warp 6 first loads the weights.)
+    const bool leader = tc::elect_one();
+    if (warp == 6 && g == 0 && leader) {          // resident weights (XFORM layers are always weight-resident)
+      const int ntile = p.nkc * p.tiles_per_kc;
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)cb * ntile * p.b_tile_bytes;
+      for (int t = 0; t < ntile; ++t) {
+        tc::mbar_arrive_expect_tx(b_full + 8 * t, p.b_tile_bytes);
+        tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
+      }
+    }
+    const int c8 = warp == 0 ? 0 : warp - 5;       // chunk 0..3
+    float ca[8], cbv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ca[j] = s_coef[c8 * 8 + j]; cbv[j] = s_coef[64 + c8 * 8 + j]; }
+    // the positions this lane touches are the same for every plane: precompute their inside-the-image flags
+    uint32_t inside_bits = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int pos = lane + 32 * i;
+      const int r = pos / TC_PW, c = pos - r * TC_PW;
+      if (pos < TC_PH * TC_PW && (unsigned)(h0 - 1 + r) < (unsigned)p.H && (unsigned)(w0 - 1 + c) < (unsigned)p.W) inside_bits |= 1u << i;
+    }
+    RingPos ld, xf;
+    int t_ld = z_lo - p.Jhi;
+    const int t_end = z_end - 1 - p.Jlo;
+    auto issue = [&]() {
+      while (t_ld <= t_end && (t_ld < 0 || t_ld >= p.Din)) ++t_ld;
+      if (t_ld > t_end) return;
+      tc::mbar_wait(a_empty + 8 * ld.idx, ld.phase ^ 1, 1);
+      if (leader) {
+        tc::mbar_arrive_expect_tx(a_full + 8 * ld.idx, p.a_stage_bytes);
+        tc::tma_load_4d(smem_a + ld.idx * p.a_stage_bytes, &tmA0, a_full + 8 * ld.idx, (w0 - 1) * 8, h0 - 1, t_ld, n * (p.C0 >> 3));
+      }
+      ld.advance(SA);
+      ++t_ld;
+    };
+    if (warp == 0) for (uint32_t i = 0; i + 2 < SA; ++i) issue();
+    for (int t = z_lo - p.Jhi; t <= t_end; ++t) {
+      if (t < 0 || t >= p.Din) continue;
+      if (warp == 0) issue();
+      DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * xf.idx, xf.phase, 8));
+      uint4* chunk = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes) + c8 * (TC_PH * TC_PW);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int pos = lane + 32 * i;
+        if (pos < TC_PH * TC_PW) {
+          float f[8];
+          unpack8<T>(chunk[pos], f);
+          const bool inside = (inside_bits >> i) & 1u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float z = fmaf(ca[j], f[j], cbv[j]); f[j] = inside ? fmaxf(z, 0.01f * z) : 0.f; }
+          chunk[pos] = pack8<T>(f);
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
+      xf.advance(SA);
+    }
+  } else if (warp == 0) {
     // ---------------- activation producer: one TMA box per (input plane, channel chunk) -----------
     const bool leader = tc::elect_one();
     RingPos a;
@@ -226,9 +307,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t col = tmem + lo_slot * CB;
         const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17), id3 = idesc0 | (((3 * CB) >> 3) << 17);
         for (int kc = 0; kc < p.nkc; ++kc) {
-          if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
+          if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           tc::tc_fence_after();
-          { const RingPos an = a.next(SA); a_peek = tc::mbar_try_wait(a_full + 8 * an.idx, an.phase); }   // result consumed after the burst
+          { const RingPos an = a.next(SA); a_peek = tc::mbar_try_wait(a_mma + 8 * an.idx, an.phase); }   // result consumed after the burst
           if (leader) {
             const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
@@ -279,7 +360,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
         const int tapmask = p.cls[c].tapmask;
         for (int kc = 0; kc < p.nkc; ++kc) {
-          if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * a.idx, a.phase, 4));
+          if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           a_peek = false;
           tc::tc_fence_after();
           const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
@@ -474,7 +555,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   __syncthreads();
   if constexpr (!TCONV) {
     if (!idle)
-      for (int i = threadIdx.x - g * TC_THREADS; i < 2 * (int)CB; i += TC_THREADS) {      // each group flushes its own tile's sums
+      for (int i = threadIdx.x - g * TPG; i < 2 * (int)CB; i += TPG) {      // each group flushes its own tile's sums
         const int c = i % (int)CB, which = i / (int)CB;
         atomicAdd(p.sums + ((size_t)n * p.Cout + (size_t)cb * CB + c) * 2 + which, (double)s_stat[i]);
       }
@@ -489,6 +570,7 @@ struct TcLayer {
   bool enabled = false;
   int ms0[6] = {0, 0, 0, 0, 0, 0}, ms1[6] = {0, 0, 0, 0, 0, 0};   // tensor-map specs {n, C, D, H, W, KC}; ms1[0] == 0 -> no second input
   bool map_bf16 = false;
+  bool xform_ok = false;          // layer shape supports norm-on-load (plain stride-1, one 32-channel chunk, resident weights)
   CUtensorMap tm0, tm1;
   void* wpack = nullptr;
   TcKParams kp{};
@@ -648,6 +730,8 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   kp.D = out_sp[0]; kp.H = out_sp[1]; kp.W = out_sp[2];
   kp.tilesH = (kp.H + TC_TH - 1) / TC_TH; kp.tilesW = (kp.W + TC_TW - 1) / TC_TW;
   kp.ncb = cout / CB; kp.SA = SA; kp.NB = NB; kp.resident = resident; kp.G = G;
+  kp.xform = 0; kp.xf_sums = nullptr; kp.xf_gamma = nullptr; kp.xf_beta = nullptr; kp.xf_inv_count = 0.f;
+  t.xform_ok = !strided && resident && c1 == 0 && KC == 32 && cin == 32 && CB <= 32 && SA >= 3;
   kp.R = std::min(TC_MAX_R, (512 / G) / CB);
   kp.fmt = bf16 ? 1 : 0;
   kp.a_stage_bytes = KC * 360; kp.b_tile_bytes = kp.jmax * CB * KC * 2;
@@ -756,22 +840,27 @@ inline int tc_prepare_tconv(TcLayer& t, const std::vector<float>& w, int cin, in
 template <typename T>
 inline int tc_set_attr_all() {
   cudaError_t e = cudaSuccess;
-#define DWMH_TC_ATTR(K, S, C, D) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, K, S, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)
+#define DWMH_TC_ATTR(K, S, C, D) if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, K, S, C, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX)
   DWMH_TC_ATTR(1, true, false, false); DWMH_TC_ATTR(2, true, false, false); DWMH_TC_ATTR(4, true, false, false);
   DWMH_TC_ATTR(1, false, false, false); DWMH_TC_ATTR(2, false, false, false); DWMH_TC_ATTR(4, false, false, false);
   DWMH_TC_ATTR(1, false, true, false); DWMH_TC_ATTR(2, false, true, false); DWMH_TC_ATTR(4, false, true, false);
   DWMH_TC_ATTR(1, true, false, true); DWMH_TC_ATTR(2, true, false, true); DWMH_TC_ATTR(4, true, false, true);
   DWMH_TC_ATTR(1, false, false, true); DWMH_TC_ATTR(2, false, false, true); DWMH_TC_ATTR(4, false, false, true);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
 #undef DWMH_TC_ATTR
   return e == cudaSuccess ? 0 : 1;
 }
 
 inline int tc_init_attributes(bool bf16) { return bf16 ? tc_set_attr_all<__nv_bfloat16>() : tc_set_attr_all<__half>(); }
 
+struct TcXform { const double* sums; const float* gamma; const float* beta; float inv_count; };
+
 template <typename T>
-int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, std::string* err) {
+int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, std::string* err, const TcXform* xf = nullptr) {
   TcKParams kp = t.kp;
   kp.sums = sums;
+  if (xf && t.xform_ok) { kp.xform = 1; kp.xf_sums = xf->sums; kp.xf_gamma = xf->gamma; kp.xf_beta = xf->beta; kp.xf_inv_count = xf->inv_count; }
   const int tiles = kp.tilesH * kp.tilesW;
   int ZB = kp.D;
   while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 2) ZB = (ZB + 1) / 2;
@@ -792,9 +881,13 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   kp.prof = prof_dev;
   const int ks = kp.KC / 16;
   const bool small = kp.CB <= 32 && !kp.tconv;
-#define DWMH_TC_LAUNCH(K, S, C, D) conv3_tc_kernel<T, K, S, C, D><<<grid, threads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
+#define DWMH_TC_LAUNCH(K, S, C, D) conv3_tc_kernel<T, K, S, C, D, false><<<grid, threads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
 #define DWMH_TC_LAUNCH_K(S, C, D) do { if (ks == 1) DWMH_TC_LAUNCH(1, S, C, D); else if (ks == 2) DWMH_TC_LAUNCH(2, S, C, D); else DWMH_TC_LAUNCH(4, S, C, D); } while (0)
-  if (kp.tconv) DWMH_TC_LAUNCH_K(false, true, false);
+  if (kp.xform) {
+    const unsigned xthreads = (TC_THREADS + 64) * kp.G;
+    if (kp.G == 2) conv3_tc_kernel<T, 2, false, false, true, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
+    else conv3_tc_kernel<T, 2, false, false, false, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
+  } else if (kp.tconv) DWMH_TC_LAUNCH_K(false, true, false);
   else if (kp.G == 2) { if (small) DWMH_TC_LAUNCH_K(true, false, true); else DWMH_TC_LAUNCH_K(false, false, true); }
   else { if (small) DWMH_TC_LAUNCH_K(true, false, false); else DWMH_TC_LAUNCH_K(false, false, false); }
 #undef DWMH_TC_LAUNCH_K
