@@ -127,7 +127,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       for (uint32_t s_ = 0; s_ < R; ++s_) { tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * s_, 1); tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * (R + s_), 4); }
       for (uint32_t s_ = 0; s_ < SA; ++s_) tc::mbar_init(bg + 16 * SA + 16 * NB + 16 * R + 8 * s_, 4);
     }
-    for (uint32_t s_ = 0; s_ < NB; ++s_) { tc::mbar_init(b_full + 8 * s_, 1); tc::mbar_init(b_empty + 8 * s_, 1); }
+    const uint32_t nactive = (uint32_t)min(p.G, p.total_items - (int)blockIdx.x * p.G);      // groups of this CTA that have a tile
+    for (uint32_t s_ = 0; s_ < NB; ++s_) { tc::mbar_init(b_full + 8 * s_, 1); tc::mbar_init(b_empty + 8 * s_, nactive); }
     tc::fence_barrier_init();
   }
   if (warp_abs == 1) tc::tmem_alloc(tc::smem_u32(tmem_ptr_smem), 512);
@@ -247,7 +248,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tc::mbar_arrive_expect_tx(b_full + 8 * t, p.b_tile_bytes);
           tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
         }
-    } else {
+    } else if (g == 0) {     // streamed weight tiles are shared by the groups of the CTA (same cout block, same plane range)
       RingPos b;
       for (int t = z_lo - p.Jhi; t <= z_end - 1 - p.Jlo; ++t) {
         if (t < 0 || t >= p.Din) continue;
@@ -701,6 +702,17 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
       }
     }
   }
+  // (1b) dual-group streaming plan: both groups consume ONE shared ring of weight tiles in lockstep (M = 256 per tile fetched)
+  for (int kc = KC0; kc >= 32 && !CB && allow_dual; kc >>= 1) {
+    const int a_stage = kc * 360;
+    for (int cbt = std::min(cout, 64); cbt >= 32; cbt -= 16) {
+      if (cout % cbt) continue;
+      if (256 / cbt < kp.jmax + 1) continue;
+      const int b_tile = kp.jmax * cbt * kc * 2;
+      const int nb = (budget - 2 * 3 * a_stage) / b_tile;
+      if (nb >= 3) { KC = kc; CB = cbt; resident = 0; SA = 3; NB = std::min(nb, TC_MAX_NB); G = 2; break; }
+    }
+  }
   // (2) single-group plans
   for (int kc = KC0; kc >= 16 && !CB; kc >>= 1) {
     const int a_stage = kc * 360, ntile = (cin / kc) * kp.tiles_per_kc;
@@ -869,7 +881,7 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   const long long items = (long long)nb * kp.ncb * kp.nzb * tiles;
   // both groups of a CTA must share the cout block whose weights are resident: pairs (2k, 2k+1) stay inside
   // one (n, cb) when the tiles x z-blocks count is even
-  if (kp.G == 2 && ((long long)kp.nzb * tiles) % 2 != 0) kp.G = 1;
+  if (kp.G == 2 && (kp.resident ? ((long long)kp.nzb * tiles) % 2 != 0 : tiles % 2 != 0)) kp.G = 1;    // (streamed weights: same z-block too)
   kp.total_items = (int)items;
   const unsigned grid = (unsigned)((items + kp.G - 1) / kp.G);
   const unsigned threads = TC_THREADS * kp.G;
