@@ -618,7 +618,7 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
         if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
         {
           Layer& P = c->layers[L.in0];
-          TcXform xf{P.sums, P.gamma_dev, P.beta_dev, 1.0f / (float)P.vout()};
+          TcXform xf{P.sums, P.gamma_dev, P.beta_dev, 1.0f / (float)P.vout(), P.out};
           DW_TRY(tc_launch<T>(L.tc, nb, L.sums, c->num_sms, st, &g_err, P.fused_norm ? &xf : nullptr));
         }
         if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }

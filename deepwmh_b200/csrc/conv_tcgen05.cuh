@@ -60,7 +60,7 @@ struct TcKParams {
   int SA, NB, resident, R, fmt;
   // norm-on-load (XFORM kernels): the input tensor is the producer's RAW fp16 output; InstanceNorm + LeakyReLU of the
   // producer are applied to each landed plane in shared memory by the two producer warps before the MMA reads it
-  const double* xf_sums; const float* xf_gamma; const float* xf_beta; float xf_inv_count; int xform;
+  const double* xf_sums; const float* xf_gamma; const float* xf_beta; float xf_inv_count; int xform; const void* xf_src;
   int G;              // work-item pipelines ("groups") per CTA: 2 = two tiles share the resident weights, each with 256 TMEM columns
   int total_items;
   unsigned long long* prof;   // dbg & 8: per-role wait/total cycle counters
@@ -81,7 +81,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t hi, uint32_t lo) { return (
 
 // KSTEPS = KC/16 (UMMA K steps per channel chunk); SMALL_CB: CB <= 32 -> per-thread running statistics.
 template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV, bool DUAL, bool XFORM>
-__global__ void __launch_bounds__((DUAL ? 2 : 1) * (XFORM ? TC_THREADS + 64 : TC_THREADS), 1)
+__global__ void __launch_bounds__((DUAL ? 2 : 1) * TC_THREADS, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const TcKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = tc::smem_u32(smem);
@@ -89,7 +89,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   // Dual-group CTA: two independent tile pipelines (own activation ring, accumulator ring, warps) share the
   // resident weight tiles; while one group's issue thread sits in barrier latency or bookkeeping the other
   // group's MMAs keep the tensor pipe busy.
-  constexpr int WPG = XFORM ? TC_WARPS_PER_GROUP + 2 : TC_WARPS_PER_GROUP;     // XFORM: two extra transform warps (7, 8)
+  constexpr int WPG = TC_WARPS_PER_GROUP;
   constexpr int TPG = WPG * 32;
   const int g = warp_abs / WPG;
   const int warp = warp_abs - g * WPG;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer, 7..8 transform
@@ -125,7 +125,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t bg = bar0 + (uint32_t)gg * nbar * 8u;
       for (uint32_t s_ = 0; s_ < SA; ++s_) { tc::mbar_init(bg + 8 * s_, 1); tc::mbar_init(bg + 8 * (SA + s_), 1); }
       for (uint32_t s_ = 0; s_ < R; ++s_) { tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * s_, 1); tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * (R + s_), 4); }
-      for (uint32_t s_ = 0; s_ < SA; ++s_) tc::mbar_init(bg + 16 * SA + 16 * NB + 16 * R + 8 * s_, 4);
+      for (uint32_t s_ = 0; s_ < SA; ++s_) tc::mbar_init(bg + 16 * SA + 16 * NB + 16 * R + 8 * s_, 2);
     }
     const uint32_t nactive = (uint32_t)min(p.G, p.total_items - (int)blockIdx.x * p.G);      // groups of this CTA that have a tile
     for (uint32_t s_ = 0; s_ < NB; ++s_) { tc::mbar_init(b_full + 8 * s_, 1); tc::mbar_init(b_empty + 8 * s_, nactive); }
@@ -153,13 +153,15 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (idle) {
     // odd item count: the second group of the last CTA has nothing to do
   } else
-  if (XFORM && (warp == 0 || warp >= 6)) {
-    // ---------------- norm-on-load: warps 0, 6, 7, 8 transform every landed plane in place ----------
-    // (plain stride-1 layer with ONE 32-channel chunk per plane: each warp owns one 8-channel chunk, its 16
-    // coefficients live in registers.  Warp 0 also issues the TMA loads SA-2 planes ahead, so that waiting for a
-    // free slot never delays the transform of the plane the MMA needs next; warp 6 first loads the weights.)
+  if (XFORM && (warp == 0 || warp == 6)) {
+    // ---------------- norm-on-load: loader warps 0 and 6 ---------------------------------------------
+    // (plain stride-1 layer with ONE 32-channel chunk per plane.)  Each warp owns two 8-channel chunks: it reads the
+    // producer's RAW fp16 plane (with halo, out-of-image lanes = 0) from global memory into registers one
+    // (plane, chunk) unit ahead, applies InstanceNorm + LeakyReLU and stores the operand once into the
+    // shared-memory stage -- no TMA and no extra shared-memory round trip (these layers are bound by the
+    // shared-memory operand bandwidth and, with many warps, by instruction issue).  Warp 6 first fetches the weights.
     const bool leader = tc::elect_one();
-    if (warp == 6 && g == 0 && leader) {          // resident weights (XFORM layers are always weight-resident)
+    if (warp == 6 && g == 0 && leader) {
       const int ntile = p.nkc * p.tiles_per_kc;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)cb * ntile * p.b_tile_bytes;
       for (int t = 0; t < ntile; ++t) {
@@ -167,54 +169,69 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
       }
     }
-    const int c8 = warp == 0 ? 0 : warp - 5;       // chunk 0..3
-    float ca[8], cbv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ca[j] = s_coef[c8 * 8 + j]; cbv[j] = s_coef[64 + c8 * 8 + j]; }
-    // the positions this lane touches are the same for every plane: precompute their inside-the-image flags
+    const int c8_0 = warp == 0 ? 0 : 2;            // chunks c8_0, c8_0 + 1
+    // the 6 box positions of this lane are the same for every plane: precompute validity and global offsets
     uint32_t inside_bits = 0;
+    int goff[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const int pos = lane + 32 * i;
       const int r = pos / TC_PW, c = pos - r * TC_PW;
-      if (pos < TC_PH * TC_PW && (unsigned)(h0 - 1 + r) < (unsigned)p.H && (unsigned)(w0 - 1 + c) < (unsigned)p.W) inside_bits |= 1u << i;
+      const bool in = pos < TC_PH * TC_PW && (unsigned)(h0 - 1 + r) < (unsigned)p.H && (unsigned)(w0 - 1 + c) < (unsigned)p.W;
+      if (in) inside_bits |= 1u << i;
+      goff[i] = in ? (h0 - 1 + r) * p.W + (w0 - 1 + c) : 0;
     }
-    RingPos ld, xf;
-    int t_ld = z_lo - p.Jhi;
+    const bool all_inside = __all_sync(0xffffffffu, inside_bits == (lane < 20 ? 0x3Fu : 0x1Fu));
+    const size_t plane_v = (size_t)p.H * p.W, chunk_v = (size_t)p.Din * plane_v;
+    const uint4* gsrc = reinterpret_cast<const uint4*>(p.xf_src) + ((size_t)n * (p.C0 >> 3) + c8_0) * chunk_v;
     const int t_end = z_end - 1 - p.Jlo;
-    auto issue = [&]() {
-      while (t_ld <= t_end && (t_ld < 0 || t_ld >= p.Din)) ++t_ld;
-      if (t_ld > t_end) return;
-      tc::mbar_wait(a_empty + 8 * ld.idx, ld.phase ^ 1, 1);
-      if (leader) {
-        tc::mbar_arrive_expect_tx(a_full + 8 * ld.idx, p.a_stage_bytes);
-        tc::tma_load_4d(smem_a + ld.idx * p.a_stage_bytes, &tmA0, a_full + 8 * ld.idx, (w0 - 1) * 8, h0 - 1, t_ld, n * (p.C0 >> 3));
-      }
-      ld.advance(SA);
-      ++t_ld;
+    auto next_valid = [&](int t) { while (t <= t_end && (t < 0 || t >= p.Din)) ++t; return t; };
+    auto load_unit = [&](int t, int k, uint4 v[6]) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        v[i] = ((inside_bits >> i) & 1u) ? ld_stream(gsrc + (size_t)k * chunk_v + (size_t)t * plane_v + goff[i]) : make_uint4(0, 0, 0, 0);
     };
-    if (warp == 0) for (uint32_t i = 0; i + 2 < SA; ++i) issue();
-    for (int t = z_lo - p.Jhi; t <= t_end; ++t) {
-      if (t < 0 || t >= p.Din) continue;
-      if (warp == 0) issue();
-      DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * xf.idx, xf.phase, 8));
-      uint4* chunk = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes) + c8 * (TC_PH * TC_PW);
+    RingPos xf;
+    uint4 nxt[6];
+    int t = next_valid(z_lo - p.Jhi);
+    if (t <= t_end) load_unit(t, 0, nxt);
+    while (t <= t_end) {
+      const int tn = next_valid(t + 1);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int pos = lane + 32 * i;
-        if (pos < TC_PH * TC_PW) {
-          float f[8];
-          unpack8<T>(chunk[pos], f);
-          const bool inside = (inside_bits >> i) & 1u;
+      for (int k = 0; k < 2; ++k) {
+        uint4 cur[6];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float z = fmaf(ca[j], f[j], cbv[j]); f[j] = inside ? fmaxf(z, 0.01f * z) : 0.f; }
-          chunk[pos] = pack8<T>(f);
+        for (int i = 0; i < 6; ++i) cur[i] = nxt[i];
+        if (k == 0) load_unit(t, 1, nxt); else if (tn <= t_end) load_unit(tn, 0, nxt);      // next unit's loads fly meanwhile
+        if (k == 0) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * xf.idx, xf.phase ^ 1, 8));
+        const int c8 = c8_0 + k;
+        float ca[8], cbv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ca[j] = s_coef[c8 * 8 + j]; cbv[j] = s_coef[64 + c8 * 8 + j]; }
+        uint4* chunk = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes) + c8 * (TC_PH * TC_PW);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int pos = lane + 32 * i;
+          if (pos < TC_PH * TC_PW) {
+            float f[8];
+            unpack8<T>(cur[i], f);
+            if (all_inside) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float z = fmaf(ca[j], f[j], cbv[j]); f[j] = fmaxf(z, 0.01f * z); }
+            } else {
+              const bool inside = (inside_bits >> i) & 1u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float z = fmaf(ca[j], f[j], cbv[j]); f[j] = inside ? fmaxf(z, 0.01f * z) : 0.f; }
+            }
+            chunk[pos] = pack8<T>(f);
+          }
         }
       }
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
       xf.advance(SA);
+      t = tn;
     }
   } else if (warp == 0) {
     // ---------------- activation producer: one TMA box per (input plane, channel chunk) -----------
@@ -742,6 +759,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   kp.D = out_sp[0]; kp.H = out_sp[1]; kp.W = out_sp[2];
   kp.tilesH = (kp.H + TC_TH - 1) / TC_TH; kp.tilesW = (kp.W + TC_TW - 1) / TC_TW;
   kp.ncb = cout / CB; kp.SA = SA; kp.NB = NB; kp.resident = resident; kp.G = G;
+  kp.xf_src = nullptr;
   kp.xform = 0; kp.xf_sums = nullptr; kp.xf_gamma = nullptr; kp.xf_beta = nullptr; kp.xf_inv_count = 0.f;
   t.xform_ok = !strided && resident && c1 == 0 && KC == 32 && cin == 32 && CB <= 32 && SA >= 3;
   kp.R = std::min(TC_MAX_R, (512 / G) / CB);
@@ -858,21 +876,21 @@ inline int tc_set_attr_all() {
   DWMH_TC_ATTR(1, false, true, false); DWMH_TC_ATTR(2, false, true, false); DWMH_TC_ATTR(4, false, true, false);
   DWMH_TC_ATTR(1, true, false, true); DWMH_TC_ATTR(2, true, false, true); DWMH_TC_ATTR(4, true, false, true);
   DWMH_TC_ATTR(1, false, false, true); DWMH_TC_ATTR(2, false, false, true); DWMH_TC_ATTR(4, false, false, true);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
 #undef DWMH_TC_ATTR
   return e == cudaSuccess ? 0 : 1;
 }
 
 inline int tc_init_attributes(bool bf16) { return bf16 ? tc_set_attr_all<__nv_bfloat16>() : tc_set_attr_all<__half>(); }
 
-struct TcXform { const double* sums; const float* gamma; const float* beta; float inv_count; };
+struct TcXform { const double* sums; const float* gamma; const float* beta; float inv_count; const void* src; };
 
 template <typename T>
 int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, std::string* err, const TcXform* xf = nullptr) {
   TcKParams kp = t.kp;
   kp.sums = sums;
-  if (xf && t.xform_ok) { kp.xform = 1; kp.xf_sums = xf->sums; kp.xf_gamma = xf->gamma; kp.xf_beta = xf->beta; kp.xf_inv_count = xf->inv_count; }
+  if (xf && t.xform_ok) { kp.xform = 1; kp.xf_sums = xf->sums; kp.xf_gamma = xf->gamma; kp.xf_beta = xf->beta; kp.xf_inv_count = xf->inv_count; kp.xf_src = xf->src; }
   const int tiles = kp.tilesH * kp.tilesW;
   int ZB = kp.D;
   while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 2) ZB = (ZB + 1) / 2;
@@ -896,9 +914,9 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
 #define DWMH_TC_LAUNCH(K, S, C, D) conv3_tc_kernel<T, K, S, C, D, false><<<grid, threads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
 #define DWMH_TC_LAUNCH_K(S, C, D) do { if (ks == 1) DWMH_TC_LAUNCH(1, S, C, D); else if (ks == 2) DWMH_TC_LAUNCH(2, S, C, D); else DWMH_TC_LAUNCH(4, S, C, D); } while (0)
   if (kp.xform) {
-    const unsigned xthreads = (TC_THREADS + 64) * kp.G;
-    if (kp.G == 2) conv3_tc_kernel<T, 2, false, false, true, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
-    else conv3_tc_kernel<T, 2, false, false, false, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
+    const unsigned xthreads = TC_THREADS * kp.G;
+    if (kp.G == 2) conv3_tc_kernel<T, 2, true, false, true, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
+    else conv3_tc_kernel<T, 2, true, false, false, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
   } else if (kp.tconv) DWMH_TC_LAUNCH_K(false, true, false);
   else if (kp.G == 2) { if (small) DWMH_TC_LAUNCH_K(true, false, true); else DWMH_TC_LAUNCH_K(false, false, true); }
   else { if (small) DWMH_TC_LAUNCH_K(true, false, false); else DWMH_TC_LAUNCH_K(false, false, false); }
