@@ -225,6 +225,24 @@ def test_ensemble_mean_of_two_models():
     _gate(ref.argmax(0), ref, got.argmax(0), got, tol=1e-2, agree=0.998, dice=0.995)
 
 
+def test_checkpoint_reload_in_one_context_matches_fresh_contexts():
+    """a13 as predict_cases does it: ONE trainer, `for p in params: trainer.load_checkpoint_ram(p, False)`."""
+    plans = small_plans()
+    data = O.synthetic_flair((40, 34, 32), seed=8)
+    data[0] = O.zscore_nnunet(data[0], np.where(data[0] != 0, 0, -1), True)
+    nets = [O.build_benchmark_network(k, plans) for k in range(2)]
+    tr, _ = _trainer(plans, model_index=0)
+    outs = []
+    for k in (0, 1, 0):
+        tr.load_checkpoint_ram({"state_dict": nets[k].state_dict()}, False)
+        outs.append(tr.predict_preprocessed_data_return_seg_and_softmax(data)[1])
+    assert np.abs(outs[0] - outs[2]).max() < 2e-3          # same weights again -> same result (statistics-order noise only)
+    assert np.abs(outs[0] - outs[1]).max() > 5e-2          # different model really loaded
+    ref1 = O.OracleTrainer(plans, nets[1]).predict_preprocessed_data_return_seg_and_softmax(data)[1]
+    assert np.abs(outs[1] - ref1).max() < 1e-2
+    tr.network.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # BASELINE.json full size (config 2): 182x218x182, 128^3 patch, 8x TTA, against the committed fixture
 # ------------------------------------------------------------------------------------------------
