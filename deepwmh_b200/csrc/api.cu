@@ -389,7 +389,22 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     for (int i = 0; i < nL; ++i) {
       Layer& L = c->layers[i];
       LaneLayer& b = ln.ll[i];
-      if (L.kind == L_FIRST) continue;
+      if (L.kind == L_FIRST) {
+        if (li == 0) {
+          tc_free(L.tc);
+          static int allow_first = -1;
+          if (allow_first < 0) { const char* e = getenv("DWMH_TC_FIRST"); allow_first = e ? atoi(e) : 1; }
+          std::string why;
+          if (allow_first && L.k[0] == 3 && L.k[1] == 3 && L.k[2] == 3 && L.c0 == 1) {
+            std::vector<float> w27((size_t)27 * L.cout);
+            for (int co = 0; co < L.cout; ++co) for (int t = 0; t < 27; ++t) w27[(size_t)t * L.cout + co] = L.w[(size_t)co * 27 + t];
+            if (tc_prepare_first(L.tc, w27, L.cout, L.out_sp, c->bf16, b.raw, &why))
+              if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
+          }
+        }
+        b.tm0 = L.tc.tm0; b.tm1 = L.tc.tm1;
+        continue;
+      }
       const void* in0 = ln.ll[L.in0].out;
       const void* in1 = L.in1 >= 0 ? ln.ll[L.in1].out : nullptr;
       const bool strided = L.kind == L_CONV && (L.s[0] != 1 || L.s[1] != 1 || L.s[2] != 1);
@@ -594,7 +609,16 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
   for (size_t li = 0; li < c->layers.size(); ++li) {
     Layer& L = c->layers[li];
     const int taps = L.k[0] * L.k[1] * L.k[2];
-    if (L.kind == L_FIRST) {
+    if (L.kind == L_FIRST && L.tc.enabled && !c->force_generic) {
+      if (hop.to(st_tc)) return fail("stream hop failed");
+      st = st_tc;
+      TcFirstSrc fs{src, metas, patch_mode, SY, SZ};
+      const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
+      if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
+      DW_TRY(tc_launch<T>(L.tc, nb, L.sums, c->num_sms, st, &g_err, nullptr, &fs));
+      if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
+      c->launches++;
+    } else if (L.kind == L_FIRST) {
       if (hop.to(st_aux)) return fail("stream hop failed");
       st = st_aux;
       FirstConvParams p;

@@ -42,6 +42,8 @@ constexpr int TC_PLANE_BYTES = TC_PH * TC_PW * 16;     // one 8-channel chunk of
 constexpr int TC_MAX_SA = 4, TC_MAX_NB = 40, TC_MAX_R = 16;
 constexpr int TC_SMEM_MAX = 232448;                    // 227 KB opt-in limit
 constexpr int TC_SMEM_RESERVED = 5120;                 // barriers + TMEM pointer + statistics
+constexpr int TC_SMEM_RESERVED_FIRST = 8192;           // FIRST kernels: + two rolling 3-slice input windows
+constexpr int TC_FIRST_STAGE_BYTES = 8 * 128 * 16;     // im2col operand of one output plane: 4 hi + 4 lo chunks of 8 taps
 
 // One parity class of a strided conv (a plain stride-1 conv has exactly one class).  The producer tensor of
 // a strided conv is stored a second time parity-split ("space to depth": [n][class][C/8][D/sd][H/sh][W/sw][8]),
@@ -61,6 +63,8 @@ struct TcKParams {
   // norm-on-load (XFORM kernels): the input tensor is the producer's RAW fp16 output; InstanceNorm + LeakyReLU of the
   // producer are applied to each landed plane in shared memory by the two producer warps before the MMA reads it
   const double* xf_sums; const float* xf_gamma; const float* xf_beta; float xf_inv_count; int xform; const void* xf_src;
+  // FIRST kernels (Cin = 1 first conv): loader warps build an im2col operand from the fp32 volume / patches
+  const float* fc_src; const SampleMeta* fc_metas; int fc_patch_mode, fc_SY, fc_SZ, first;
   int G;              // work-item pipelines ("groups") per CTA: 2 = two tiles share the resident weights, each with 256 TMEM columns
   int total_items;
   unsigned long long* prof;   // dbg & 8: per-role wait/total cycle counters
@@ -79,9 +83,17 @@ struct RingPos {
 
 __device__ __forceinline__ uint64_t tc_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
+// start-address shift (16-byte units) of in-plane tap sft = dy*3 + dx inside a haloed 18 x 10 plane, 5 bits per tap
+constexpr uint64_t tc_tap_shift_table() {
+  uint64_t v = 0;
+  for (int sft = 0; sft < 9; ++sft) v |= (uint64_t)((sft / 3) * TC_PW + (sft % 3)) << (5 * sft);
+  return v;
+}
+constexpr uint64_t kTapShift = tc_tap_shift_table();
+
 // KSTEPS = KC/16 (UMMA K steps per channel chunk); SMALL_CB: CB <= 32 -> per-thread running statistics.
-template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV, bool DUAL, bool XFORM>
-__global__ void __launch_bounds__((DUAL ? 2 : 1) * TC_THREADS, 1)
+template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV, bool DUAL, bool XFORM, bool FIRST = false>
+__global__ void __launch_bounds__(FIRST ? 512 : (DUAL ? 2 : 1) * TC_THREADS, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const TcKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = tc::smem_u32(smem);
@@ -91,8 +103,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   // group's MMAs keep the tensor pipe busy.
   constexpr int WPG = TC_WARPS_PER_GROUP;
   constexpr int TPG = WPG * 32;
-  const int g = warp_abs / WPG;
-  const int warp = warp_abs - g * WPG;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer, 7..8 transform
+  const bool fetcher = FIRST && warp_abs >= 2 * WPG;                  // FIRST kernels run 16 warps: 14, 15 fetch the input slices
+  const int g = fetcher ? warp_abs - 2 * WPG : warp_abs / WPG;
+  const int warp = fetcher ? 7 : warp_abs - g * WPG;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer, 7 slice fetcher
 
   int wi = blockIdx.x * p.G + g;
   const bool idle = wi >= p.total_items;
@@ -112,21 +125,31 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const uint32_t b_full = bar0 + 16u * SA, b_empty = b_full + 8u * NB;             // weight ring: shared, lives in group 0's block
   const uint32_t acc_full = bar + 16u * SA + 16u * NB, acc_empty = acc_full + 8u * R;
   const uint32_t a_ready = acc_empty + 8u * R;          // XFORM: plane transformed, ready for the MMA
-  const uint32_t a_mma = XFORM ? a_ready : a_full;      // what the MMA issuer waits on
+  const uint32_t a_mma = (XFORM || FIRST) ? a_ready : a_full;      // what the MMA issuer waits on
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * nbar * p.G);
   float* s_stat = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)g * 2 * CB;   // [2][CB] per group
   float* s_coef = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)g * 2 * 64;   // XFORM: a[64], b[64]
+  float* s_slice = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)p.G * 2 * 64 + (size_t)g * 4 * TC_PH * TC_PW;   // FIRST: 4-slot ring of haloed input slices
   const uint32_t smem_a = smem_base + (uint32_t)g * SA * p.a_stage_bytes;          // this group's activation ring
+  const uint32_t s_full = smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + (uint32_t)g * 64u, s_empty = s_full + 32u;   // FIRST: slice ring barriers
 
   if (threadIdx.x == 0) {
-    tc::prefetch_tensormap(&tmA0);
-    tc::prefetch_tensormap(&tmA1);
+    if constexpr (!FIRST) {
+      tc::prefetch_tensormap(&tmA0);
+      tc::prefetch_tensormap(&tmA1);
+    }
     for (int gg = 0; gg < p.G; ++gg) {
       const uint32_t bg = bar0 + (uint32_t)gg * nbar * 8u;
       for (uint32_t s_ = 0; s_ < SA; ++s_) { tc::mbar_init(bg + 8 * s_, 1); tc::mbar_init(bg + 8 * (SA + s_), 1); }
       for (uint32_t s_ = 0; s_ < R; ++s_) { tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * s_, 1); tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * (R + s_), 4); }
       for (uint32_t s_ = 0; s_ < SA; ++s_) tc::mbar_init(bg + 16 * SA + 16 * NB + 16 * R + 8 * s_, 2);
     }
+    if constexpr (FIRST)
+      for (int gg = 0; gg < p.G; ++gg)
+        for (uint32_t s_ = 0; s_ < 4; ++s_) {
+          tc::mbar_init(smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + gg * 64 + 8 * s_, 1);
+          tc::mbar_init(smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + gg * 64 + 32 + 8 * s_, 2);
+        }
     const uint32_t nactive = (uint32_t)min(p.G, p.total_items - (int)blockIdx.x * p.G);      // groups of this CTA that have a tile
     for (uint32_t s_ = 0; s_ < NB; ++s_) { tc::mbar_init(b_full + 8 * s_, 1); tc::mbar_init(b_empty + 8 * s_, nactive); }
     tc::fence_barrier_init();
@@ -153,7 +176,112 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   if (idle) {
     // odd item count: the second group of the last CTA has nothing to do
   } else
-  if (XFORM && (warp == 0 || warp == 6)) {
+  if (FIRST && warp == 7) {
+    // ---------------- first conv (Cin = 1): slice fetcher (extra warps 14, 15 of the CTA) ------------
+    // Streams the haloed 18 x 10 input slices of this tile (zero outside the patch, tile origin and mirror flip applied
+    // to the source index) into a 4-slot ring, each value already split x = hi + lo: low half = hi (x truncated to the
+    // 16-bit format, exact), high half = lo = rn(x - hi).  A warp of its own because the builders' proxy fence
+    // (MEMBAR + FENCE.VIEW.ASYNC) waits for every outstanding global load of the executing warp: with the prefetch in
+    // the builder warps each plane cost one full HBM latency.
+    int ox = 0, oy = 0, oz = 0, flip = 0;
+    const float* src = p.fc_src;
+    int SY = p.fc_SY, SZ = p.fc_SZ;
+    if (p.fc_patch_mode) { src += (size_t)n * p.D * p.H * p.W; SY = p.H; SZ = p.W; }
+    else { const SampleMeta m_ = p.fc_metas[n]; ox = m_.ox; oy = m_.oy; oz = m_.oz; flip = m_.flip; }
+    int sgoff[6]; bool sin_[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int pos = lane + 32 * i;
+      const int r = pos / TC_PW, c = pos - r * TC_PW;
+      const int hh = h0 - 1 + r, ww = w0 - 1 + c;
+      sin_[i] = pos < TC_PH * TC_PW && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
+      const int sj = oy + ((flip & 2) ? p.H - 1 - hh : hh), sk = oz + ((flip & 1) ? p.W - 1 - ww : ww);
+      sgoff[i] = sin_[i] ? sj * SZ + sk : 0;
+    }
+    const float* sbase = src + (size_t)ox * SY * SZ;
+    const int zstep = (flip & 4) ? -SY * SZ : SY * SZ;
+    if (flip & 4) sbase += (size_t)(p.D - 1) * SY * SZ;
+    const int nslices = z_end - z_lo + 2;                       // slice k = patch plane z_lo - 1 + k
+    constexpr uint32_t kHiMask = ActT<T>::kUmmaFormat == 0 ? 0xFFFFE000u : 0xFFFF0000u;
+    uint32_t* ring = reinterpret_cast<uint32_t*>(s_slice);
+    auto fetch = [&](int k, float v[6]) {
+      const int zz = z_lo - 1 + k;
+      const bool zin = k < nslices && (unsigned)zz < (unsigned)p.D;
+      const float* sp = sbase + (ptrdiff_t)zz * zstep;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) v[i] = (zin && sin_[i]) ? __ldg(sp + sgoff[i]) : 0.f;
+    };
+    auto step = [&](int k, float (&v)[6]) {
+      if (k >= 4) tc::mbar_wait(s_empty + 8 * (k & 3), ((k >> 2) & 1) ^ 1, 10);
+      uint32_t* dst = ring + (k & 3) * (TC_PH * TC_PW);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const float hf = __uint_as_float(__float_as_uint(v[i]) & kHiMask);
+        if (lane + 32 * i < TC_PH * TC_PW) dst[lane + 32 * i] = ActT<T>::from_f2(hf, v[i] - hf);
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(s_full + 8 * (k & 3));
+      fetch(k + 4, v);                                          // HBM latency is several planes long: 4 slices in flight
+    };
+    float v0[6], v1[6], v2[6], v3[6];
+    fetch(0, v0); fetch(1, v1); fetch(2, v2); fetch(3, v3);
+    for (int k = 0; k < nslices; k += 4) {
+      step(k, v0);
+      if (k + 1 < nslices) step(k + 1, v1);
+      if (k + 2 < nslices) step(k + 2, v2);
+      if (k + 3 < nslices) step(k + 3, v3);
+    }
+  } else if (FIRST && (warp == 0 || warp == 6)) {
+    // ---------------- first conv (Cin = 1): builder warps write the im2col operand -------------------
+    // Row m of the operand = output voxel (h0 + m/8, w0 + m%8) of plane t, columns = its 27 neighbours (hi halves in
+    // chunks 0..3, lo halves in chunks 4..7), so that x*w = hi*w_hi + lo*w_hi + hi*w_lo keeps fp32-level accuracy on
+    // the tensor cores (K = 3 x 32).  Stage layout: [8 chunks][128 rows][16 B]  (K-major, SBO = 128 B, LBO = 2048 B).
+    const bool leader = tc::elect_one();
+    if (warp == 6 && g == 0 && leader) {
+      tc::mbar_arrive_expect_tx(b_full, p.b_tile_bytes);
+      tc::bulk_load(smem_base + p.off_b, p.wpack, p.b_tile_bytes, b_full);
+    }
+    const int l64 = (warp == 0 ? 0 : 32) + lane;
+    const uint32_t* ring = reinterpret_cast<const uint32_t*>(s_slice);
+    tc::mbar_wait(s_full, 0, 11);
+    tc::mbar_wait(s_full + 8, 0, 11);
+    RingPos xf;
+    for (int j = 0; j < z_end - z_lo; ++j) {                    // plane t = z_lo + j reads slices j, j+1, j+2
+      DWMH_TIMED_WAIT(w1_, tc::mbar_wait(s_full + 8 * ((j + 2) & 3), ((j + 2) >> 2) & 1, 11));
+      tc::mbar_wait(a_empty + 8 * xf.idx, xf.phase ^ 1, 9);
+      uint4* stage = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes);
+      const uint32_t* sl[3] = {ring + (j & 3) * (TC_PH * TC_PW), ring + ((j + 1) & 3) * (TC_PH * TC_PW), ring + ((j + 2) & 3) * (TC_PH * TC_PW)};
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int m = l64 + 64 * rr;
+        const int hh = m >> 3, ww = m & 7;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          uint32_t x[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int tap = 2 * q + e;
+            if (tap < 27) {
+              const int dz = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+              x[e] = sl[dz][(hh + kh) * TC_PW + (ww + kw)];
+            } else x[e] = 0u;
+          }
+          hi[q] = __byte_perm(x[0], x[1], 0x5410);
+          lo[q] = __byte_perm(x[0], x[1], 0x7632);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          stage[c * 128 + m] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+          stage[(4 + c) * 128 + m] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+        }
+      }
+      DWMH_TIMED_WAIT(w0_, tc::fence_proxy_async());
+      __syncwarp();
+      if (lane == 0) { tc::mbar_arrive(a_ready + 8 * xf.idx); tc::mbar_arrive(s_empty + 8 * (j & 3)); }
+      xf.advance(SA);
+    }
+  } else if (XFORM && (warp == 0 || warp == 6)) {
     // ---------------- norm-on-load: loader warps 0 and 6 ---------------------------------------------
     // (plain stride-1 layer with ONE 32-channel chunk per plane.)  Each warp owns two 8-channel chunks: it reads the
     // producer's RAW fp16 plane (with halo, out-of-image lanes = 0) from global memory into registers one
@@ -292,6 +420,32 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // unrolled burst of 9 taps x KSTEPS per channel chunk in the steady state of a stride-1 layer.
     const bool elected = tc::elect_one();
     const bool leader = elected && !(p.dbg & 2);
+    if constexpr (FIRST) {
+      // one output plane per step: 6 MMAs (hi*w_hi, lo*w_hi, hi*w_lo; K = 32 each) into the plane's own slot
+      const uint32_t idesc = tc::instr_desc_f16(p.fmt, 128, (int)CB);
+      const uint32_t hi_desc = (128u >> 4) | (1u << 14);                  // SBO = 128 B for both operands
+      const uint32_t a_lbo = (2048u >> 4) << 16, b_lbo = ((CB * 16u) >> 4) << 16;
+      const uint32_t b_lo0 = ((smem_base + p.off_b) >> 4) | b_lbo;
+      tc::mbar_wait(b_full, 0, 5);
+      RingPos a, fresh, done;
+      for (int t = z_lo; t < z_end; ++t) {
+        tc::mbar_wait(acc_empty + 8 * fresh.idx, fresh.phase ^ 1, 3);
+        tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4);
+        tc::tc_fence_after();
+        if (leader) {
+          const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo;
+          const uint32_t col = tmem + fresh.idx * CB;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int achunk = (i == 0 || i == 4) ? 0 : (i == 1 || i == 5) ? 2 : (i == 2 ? 4 : 6);     // hi, hi, lo, lo, hi, hi
+            tc::umma_f16(col, tc_desc(hi_desc, a_lo0 + achunk * (2048 >> 4)), tc_desc(hi_desc, b_lo0 + i * 2 * CB), idesc, i == 0 ? 0u : 1u);
+          }
+        }
+        if (elected) { tc::umma_commit(a_empty + 8 * a.idx); tc::umma_commit(acc_full + 8 * done.idx); }
+        a.advance(SA); fresh.advance(R); done.advance(R);
+        __syncwarp();
+      }
+    } else {
     const uint32_t idesc0 = tc::instr_desc_f16(p.fmt, 128, 0);
     const uint32_t idesc1 = idesc0 | ((CB >> 3) << 17);
     const uint32_t b_lbo16 = (uint32_t)p.jmax * CB;                    // LBO of the weight tiles, in 16-B units
@@ -327,7 +481,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int kc = 0; kc < p.nkc; ++kc) {
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           tc::tc_fence_after();
-          { const RingPos an = a.next(SA); a_peek = tc::mbar_try_wait(a_mma + 8 * an.idx, an.phase); }   // result consumed after the burst
+          { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }   // result consumed after the burst
           if (leader) {
             const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
@@ -350,6 +504,62 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           a.advance(SA);
         }
         if (elected) tc::umma_commit(acc_full + 8 * done.idx);        // output plane t-1 is complete
+        done.advance(R);
+        ++next_done;
+        __syncwarp();
+        continue;
+      }
+      if (p.Jlo == 0 && zo_lo == t && zo_hi == t + 1 && fresh_from == zo_hi && 2 * CB <= 256) {
+        // ---- steady state of a depth-strided conv: sub-plane t feeds output t (all classes) and t+1 (odd-depth
+        // classes, N = 2 CB); exactly output t+1 is new.  No segment bookkeeping, two MMAs only at the ring wrap.
+        const uint32_t col0 = tmem + lo_slot * CB, col1 = (lo_slot + 1 == R) ? tmem : col0 + CB;
+        const bool wrap = lo_slot + 1 == R;
+        const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17);
+        bool fresh_pending = true;
+        for (int c = 0; c < p.nclass; ++c) {
+          const int jc = p.cls[c].jcnt, tapmask = p.cls[c].tapmask;
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
+            tc::tc_fence_after();
+            { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
+            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0) * tile16;
+            for (int m = tapmask; m; m &= m - 1) {
+              const int sft = __ffs(m) - 1;
+              uint32_t b_lo0;
+              if (p.resident) { b_lo0 = b_res; b_res += tile16; }
+              else {
+                if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
+                tc::tc_fence_after();
+                b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+                { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
+              }
+              const uint32_t a_lo1 = a_lo0 + (uint32_t)((kTapShift >> (5 * sft)) & 31u);
+              if (leader) {
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  const uint64_t adesc = tc_desc(a_hi, a_lo1 + kk * (2 * TC_PLANE_BYTES >> 4));
+                  const uint32_t bl = b_lo0 + kk * kstep_b;
+                  if (jc == 2) {
+                    const bool fr = fresh_pending && kk == 0;
+                    if (wrap || fr) {
+                      tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), idesc1, 1u);
+                      tc::umma_f16(col1, adesc, tc_desc(b_hi, bl + CB), idesc1, fr ? 0u : 1u);
+                    } else tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), id2, 1u);
+                  } else tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), idesc1, 1u);
+                }
+              }
+              if (jc == 2) fresh_pending = false;
+              if (!p.resident) {
+                if (elected) tc::umma_commit(b_empty + 8 * b.idx);
+                b.advance(NB);
+              }
+            }
+            if (elected) tc::umma_commit(a_empty + 8 * a.idx);
+            a.advance(SA);
+          }
+        }
+        if (elected) tc::umma_commit(acc_full + 8 * done.idx);        // output plane t is complete
         done.advance(R);
         ++next_done;
         __syncwarp();
@@ -391,9 +601,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
               tc::tc_fence_after();
               b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
-              { const RingPos bn = b.next(NB); b_peek = tc::mbar_try_wait(b_full + 8 * bn.idx, bn.phase); }   // consumed at the next tap
+              { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }   // consumed at the next tap
             }
-            const uint32_t a_lo1 = a_lo0 + (uint32_t)((sft / 3) * TC_PW + (sft % 3));
+            const uint32_t a_lo1 = a_lo0 + (uint32_t)((kTapShift >> (5 * sft)) & 31u);
             if (first_mma) {
               // first MMA of the step: slot by slot, overwriting (accumulate = 0) first-touched slots
               for (uint32_t i = 0; i < cnt; ++i) {
@@ -431,6 +641,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
       __syncwarp();
     }
+    }   // !FIRST
   } else {
     // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ---------------------------
     const int q = warp_abs & 3;       // TMEM lane quarter is fixed by the hardware warp id
@@ -867,6 +1078,59 @@ inline int tc_prepare_tconv(TcLayer& t, const std::vector<float>& w, int cin, in
   return 0;
 }
 
+// First conv (Cin = 1, 3x3x3, stride 1): the loader warps of the FIRST kernel build the [128 voxels][32 taps] im2col
+// operand of every output plane from the fp32 volume (tile origin + mirror flip applied on the fly); input and weights
+// are split hi + lo into two fp16 (bf16) values, so the 6 MMAs per plane (hi*w_hi, lo*w_hi, hi*w_lo) reproduce the fp32
+// product to ~2^-22.  w27 = weights as [tap][Cout] (tap = (kd*3 + kh)*3 + kw).
+inline int tc_prepare_first(TcLayer& t, const std::vector<float>& w27, int cout, const int sp[3], bool bf16, void* out, std::string* why) {
+  t.enabled = false;
+  why->clear();
+  if (cout != 16 && cout != 32) return 0;
+  TcKParams& kp = t.kp;
+  kp = TcKParams{};
+  kp.first = 1;
+  kp.nclass = 1; kp.Jlo = 0; kp.Jhi = 0; kp.jmax = 1; kp.tiles_per_kc = 1; kp.Din = sp[0];
+  kp.cls[0] = TcClassDesc{1 << 4, 0, 1, 0};
+  kp.C0 = 8; kp.C1 = 0; kp.Cout = cout; kp.CB = cout; kp.KC = 32; kp.nkc = 1; kp.nkc0 = 1;
+  kp.D = sp[0]; kp.H = sp[1]; kp.W = sp[2];
+  kp.tilesH = (kp.H + TC_TH - 1) / TC_TH; kp.tilesW = (kp.W + TC_TW - 1) / TC_TW;
+  kp.ncb = 1; kp.SA = TC_MAX_SA; kp.NB = 1; kp.resident = 1;
+  kp.R = std::min(TC_MAX_R, 256 / cout); kp.fmt = bf16 ? 1 : 0; kp.G = 2;
+  kp.a_stage_bytes = TC_FIRST_STAGE_BYTES; kp.b_tile_bytes = 12 * cout * 16;
+  kp.off_b = kp.G * kp.SA * kp.a_stage_bytes;
+  kp.off_bar = (kp.off_b + kp.b_tile_bytes + 127) & ~127u;
+  t.smem_bytes = kp.off_bar + TC_SMEM_RESERVED_FIRST;
+  if (t.smem_bytes > TC_SMEM_MAX) { *why = "internal: shared memory plan exceeds 227 KB"; return 1; }
+  kp.out = out;
+  // B tile: [12 k8 chunks][cout rows][8]: K blocks of 16 taps = w_hi(0-15), w_hi(16-31), w_hi(0-15), w_hi(16-31), w_lo(0-15), w_lo(16-31)
+  auto from_bits = [&](uint16_t b) -> float {
+    if (bf16) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+    __half h; memcpy(&h, &b, 2); return __half2float(h);
+  };
+  std::vector<uint16_t> pk((size_t)12 * cout * 8, 0);
+  for (int kb = 0; kb < 6; ++kb)
+    for (int k8 = 0; k8 < 2; ++k8)
+      for (int co = 0; co < cout; ++co)
+        for (int e = 0; e < 8; ++e) {
+          const int tap = (kb & 1) * 16 + k8 * 8 + e;
+          uint16_t v = 0;
+          if (tap < 27) {
+            const float wf = w27[(size_t)tap * cout + co];
+            const uint16_t hi = tc_to_bits(wf, bf16);
+            v = kb < 4 ? hi : tc_to_bits(wf - from_bits(hi), bf16);
+          }
+          pk[((size_t)(kb * 2 + k8) * cout + co) * 8 + e] = v;
+        }
+  if (cudaMalloc(&t.wpack, pk.size() * 2) != cudaSuccess) { *why = "cudaMalloc(wpack) failed"; return 1; }
+  if (cudaMemcpy(t.wpack, pk.data(), pk.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *why = "cudaMemcpy(wpack) failed"; return 1; }
+  kp.wpack = t.wpack;
+  t.map_bf16 = bf16;
+  t.ms0[0] = 0; t.ms1[0] = 0;
+  memset(&t.tm0, 0, sizeof t.tm0); memset(&t.tm1, 0, sizeof t.tm1);
+  t.enabled = true;
+  return 0;
+}
+
 template <typename T>
 inline int tc_set_attr_all() {
   cudaError_t e = cudaSuccess;
@@ -878,6 +1142,7 @@ inline int tc_set_attr_all() {
   DWMH_TC_ATTR(1, false, false, true); DWMH_TC_ATTR(2, false, false, true); DWMH_TC_ATTR(4, false, false, true);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3_tc_kernel<T, 2, true, false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
 #undef DWMH_TC_ATTR
   return e == cudaSuccess ? 0 : 1;
 }
@@ -885,11 +1150,16 @@ inline int tc_set_attr_all() {
 inline int tc_init_attributes(bool bf16) { return bf16 ? tc_set_attr_all<__nv_bfloat16>() : tc_set_attr_all<__half>(); }
 
 struct TcXform { const double* sums; const float* gamma; const float* beta; float inv_count; const void* src; };
+struct TcFirstSrc { const float* src; const SampleMeta* metas; int patch_mode, SY, SZ; };
 
 template <typename T>
-int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, std::string* err, const TcXform* xf = nullptr) {
+int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, std::string* err, const TcXform* xf = nullptr, const TcFirstSrc* fs = nullptr) {
   TcKParams kp = t.kp;
   kp.sums = sums;
+  if (kp.first) {
+    if (!fs) { if (err) *err = "first-conv launch without a source"; return 1; }
+    kp.fc_src = fs->src; kp.fc_metas = fs->metas; kp.fc_patch_mode = fs->patch_mode; kp.fc_SY = fs->SY; kp.fc_SZ = fs->SZ;
+  }
   if (xf && t.xform_ok) { kp.xform = 1; kp.xf_sums = xf->sums; kp.xf_gamma = xf->gamma; kp.xf_beta = xf->beta; kp.xf_inv_count = xf->inv_count; kp.xf_src = xf->src; }
   const int tiles = kp.tilesH * kp.tilesW;
   int ZB = kp.D;
@@ -899,7 +1169,7 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   const long long items = (long long)nb * kp.ncb * kp.nzb * tiles;
   // both groups of a CTA must share the cout block whose weights are resident: pairs (2k, 2k+1) stay inside
   // one (n, cb) when the tiles x z-blocks count is even
-  if (kp.G == 2 && (kp.resident ? ((long long)kp.nzb * tiles) % 2 != 0 : tiles % 2 != 0)) kp.G = 1;    // (streamed weights: same z-block too)
+  if (!kp.first && kp.G == 2 && (kp.resident ? ((long long)kp.nzb * tiles) % 2 != 0 : tiles % 2 != 0)) kp.G = 1;    // (streamed weights: same z-block too)
   kp.total_items = (int)items;
   const unsigned grid = (unsigned)((items + kp.G - 1) / kp.G);
   const unsigned threads = TC_THREADS * kp.G;
@@ -913,7 +1183,8 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   const bool small = kp.CB <= 32 && !kp.tconv;
 #define DWMH_TC_LAUNCH(K, S, C, D) conv3_tc_kernel<T, K, S, C, D, false><<<grid, threads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
 #define DWMH_TC_LAUNCH_K(S, C, D) do { if (ks == 1) DWMH_TC_LAUNCH(1, S, C, D); else if (ks == 2) DWMH_TC_LAUNCH(2, S, C, D); else DWMH_TC_LAUNCH(4, S, C, D); } while (0)
-  if (kp.xform) {
+  if (kp.first) conv3_tc_kernel<T, 2, true, false, true, false, true><<<grid, 512, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
+  else if (kp.xform) {
     const unsigned xthreads = TC_THREADS * kp.G;
     if (kp.G == 2) conv3_tc_kernel<T, 2, true, false, true, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
     else conv3_tc_kernel<T, 2, true, false, false, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
@@ -929,8 +1200,8 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
     cudaStreamSynchronize(st);
     cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost);
     const double g = (double)grid;
-    fprintf(stderr, "tcprof C0=%d C1=%d Cout=%d CB=%d KC=%d D=%d res=%d grid=%u planes/cta=%d | act-prod wait_empty %.0f tot %.0f | mma wait_a %.0f wait_acc/b %.0f tot %.0f | epi wait_full %.0f tot %.0f | w-prod wait %.0f tot %.0f (cycles per CTA)\n",
-            kp.C0, kp.C1, kp.Cout, kp.CB, kp.KC, kp.D, kp.resident, grid, kp.ZB, h[0] / g, h[2] / g, h[4] / g, h[5] / g, h[6] / g, h[8] / g, h[10] / g, h[12] / g, h[14] / g);
+    fprintf(stderr, "tcprof C0=%d C1=%d Cout=%d CB=%d KC=%d D=%d res=%d grid=%u planes/cta=%d | act-prod wait_empty %.0f w1 %.0f tot %.0f | mma wait_a %.0f wait_acc/b %.0f tot %.0f | epi wait_full %.0f tot %.0f | w-prod wait %.0f tot %.0f (cycles per CTA)\n",
+            kp.C0, kp.C1, kp.Cout, kp.CB, kp.KC, kp.D, kp.resident, grid, kp.ZB, h[0] / g, h[1] / g, h[2] / g, h[4] / g, h[5] / g, h[6] / g, h[8] / g, h[10] / g, h[12] / g, h[14] / g);
   }
   return 0;
 }
