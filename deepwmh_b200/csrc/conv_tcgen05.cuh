@@ -93,7 +93,7 @@ constexpr uint64_t kTapShift = tc_tap_shift_table();
 
 // KSTEPS = KC/16 (UMMA K steps per channel chunk); SMALL_CB: CB <= 32 -> per-thread running statistics.
 template <typename T, int KSTEPS, bool SMALL_CB, bool TCONV, bool DUAL, bool XFORM, bool FIRST = false>
-__global__ void __launch_bounds__(FIRST ? 512 : (DUAL ? 2 : 1) * TC_THREADS, 1)
+__global__ void __launch_bounds__((DUAL ? 2 : 1) * (TC_THREADS + ((FIRST || XFORM) ? 32 : 0)), 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const TcKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t smem_base = tc::smem_u32(smem);
@@ -103,9 +103,10 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   // group's MMAs keep the tensor pipe busy.
   constexpr int WPG = TC_WARPS_PER_GROUP;
   constexpr int TPG = WPG * 32;
-  const bool fetcher = FIRST && warp_abs >= 2 * WPG;                  // FIRST kernels run 16 warps: 14, 15 fetch the input slices
-  const int g = fetcher ? warp_abs - 2 * WPG : warp_abs / WPG;
-  const int warp = fetcher ? 7 : warp_abs - g * WPG;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer, 7 slice fetcher
+  constexpr int NG = DUAL ? 2 : 1;
+  const bool extra = (FIRST || XFORM) && warp_abs >= NG * WPG;        // FIRST / XFORM kernels run one more warp per group
+  const int g = extra ? warp_abs - NG * WPG : warp_abs / WPG;
+  const int warp = extra ? 7 : warp_abs - g * WPG;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer, 7 slice fetcher (FIRST) / transform (XFORM)
 
   int wi = blockIdx.x * p.G + g;
   const bool idle = wi >= p.total_items;
@@ -170,7 +171,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem + (uint32_t)g * 256u;       // group 1 owns TMEM columns 256..511
   const bool prof_on = (p.dbg & 8) != 0;
-  long long w0_ = 0, w1_ = 0;
+  long long w0_ = 0, w1_ = 0, w2_ = 0, w3_ = 0, w4_ = 0;
   const long long tstart_ = clock64();
 
   if (idle) {
@@ -281,13 +282,13 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       if (lane == 0) { tc::mbar_arrive(a_ready + 8 * xf.idx); tc::mbar_arrive(s_empty + 8 * (j & 3)); }
       xf.advance(SA);
     }
-  } else if (XFORM && (warp == 0 || warp == 6)) {
-    // ---------------- norm-on-load: loader warps 0 and 6 ---------------------------------------------
-    // (plain stride-1 layer with ONE 32-channel chunk per plane.)  Each warp owns two 8-channel chunks: it reads the
-    // producer's RAW fp16 plane (with halo, out-of-image lanes = 0) from global memory into registers one
-    // (plane, chunk) unit ahead, applies InstanceNorm + LeakyReLU and stores the operand once into the
-    // shared-memory stage -- no TMA and no extra shared-memory round trip (these layers are bound by the
-    // shared-memory operand bandwidth and, with many warps, by instruction issue).  Warp 6 first fetches the weights.
+  } else if (XFORM && (warp == 6 || warp == 7)) {
+    // ---------------- norm-on-load: transform warps 6 and 7 (7 = extra warp of the group) -----------
+    // (plain stride-1 layer, 32-channel chunks, <= 64 input channels.)  The TMA producer (warp 0) lands the producer
+    // layer's RAW fp16 plane; these two warps apply InstanceNorm + LeakyReLU to it IN PLACE in shared memory (two
+    // 8-channel chunks each; out-of-image halo positions must stay exactly 0), publish it to the async proxy and
+    // signal a_ready.  TMA keeps several planes in flight without holding registers -- with register prefetch
+    // (LDG -> transform -> STS) one plane in flight per warp left the loaders bound by the HBM latency.
     const bool leader = tc::elect_one();
     if (warp == 6 && g == 0 && leader) {
       const int ntile = p.nkc * p.tiles_per_kc;
@@ -297,69 +298,66 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
       }
     }
-    const int c8_0 = warp == 0 ? 0 : 2;            // chunks c8_0, c8_0 + 1
-    // the 6 box positions of this lane are the same for every plane: precompute validity and global offsets
+    // Each warp owns two adjacent 8-channel chunks = one contiguous, 128-byte aligned run of 360 16-byte slots; lane l
+    // handles slots l, l + 32, ... so that every quarter-warp touches one aligned 128-byte line (chunk bases alone
+    // are only 64-byte aligned: per-chunk indexing cost two shared-memory wavefronts per access).
+    const int c8_0 = warp == 6 ? 0 : 2;            // chunks c8_0 (slots 0..179), c8_0 + 1 (slots 180..359)
+    constexpr int NPOS = TC_PH * TC_PW, NSLOT = 2 * NPOS, NIT = (NSLOT + 31) / 32;      // 180, 360, 12
     uint32_t inside_bits = 0;
-    int goff[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int pos = lane + 32 * i;
+    for (int i = 0; i < NIT; ++i) {
+      const int idx = lane + 32 * i;
+      const int pos = idx >= NPOS ? idx - NPOS : idx;
       const int r = pos / TC_PW, c = pos - r * TC_PW;
-      const bool in = pos < TC_PH * TC_PW && (unsigned)(h0 - 1 + r) < (unsigned)p.H && (unsigned)(w0 - 1 + c) < (unsigned)p.W;
-      if (in) inside_bits |= 1u << i;
-      goff[i] = in ? (h0 - 1 + r) * p.W + (w0 - 1 + c) : 0;
+      if (idx < NSLOT && (unsigned)(h0 - 1 + r) < (unsigned)p.H && (unsigned)(w0 - 1 + c) < (unsigned)p.W) inside_bits |= 1u << i;
     }
-    const bool all_inside = __all_sync(0xffffffffu, inside_bits == (lane < 20 ? 0x3Fu : 0x1Fu));
-    const size_t plane_v = (size_t)p.H * p.W, chunk_v = (size_t)p.Din * plane_v;
-    const uint4* gsrc = reinterpret_cast<const uint4*>(p.xf_src) + ((size_t)n * (p.C0 >> 3) + c8_0) * chunk_v;
+    const uint32_t full_bits = (lane < NSLOT - 32 * (NIT - 1)) ? (1u << NIT) - 1 : (1u << (NIT - 1)) - 1;
+    const bool all_inside = __all_sync(0xffffffffu, inside_bits == full_bits);
+    const bool second = lane >= NPOS - 32 * (NPOS / 32);          // in the mixed iteration (i = NPOS / 32) lanes >= 20 are in the second chunk
     const int t_end = z_end - 1 - p.Jlo;
-    auto next_valid = [&](int t) { while (t <= t_end && (t < 0 || t >= p.Din)) ++t; return t; };
-    auto load_unit = [&](int t, int k, uint4 v[6]) {
-#pragma unroll
-      for (int i = 0; i < 6; ++i)
-        v[i] = ((inside_bits >> i) & 1u) ? ld_stream(gsrc + (size_t)k * chunk_v + (size_t)t * plane_v + goff[i]) : make_uint4(0, 0, 0, 0);
-    };
+    float a0[8], a1[8], b0[8], b1[8];
+    int cur_kc = -1;
     RingPos xf;
-    uint4 nxt[6];
-    int t = next_valid(z_lo - p.Jhi);
-    if (t <= t_end) load_unit(t, 0, nxt);
-    while (t <= t_end) {
-      const int tn = next_valid(t + 1);
+    for (int t = z_lo - p.Jhi; t <= t_end; ++t) {
+      if (t < 0 || t >= p.Din) continue;
+      for (int kc = 0; kc < p.nkc; ++kc) {
+        DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * xf.idx, xf.phase, 8));
+        uint4* run = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes) + c8_0 * NPOS;
+        if (kc != cur_kc) {                                       // coefficients of the warp's two chunks, in registers
+          cur_kc = kc;
+          const float* co = s_coef + (kc * 4 + c8_0) * 8;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        uint4 cur[6];
+          for (int j = 0; j < 8; ++j) { a0[j] = co[j]; a1[j] = co[8 + j]; b0[j] = co[64 + j]; b1[j] = co[72 + j]; }
+        }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) cur[i] = nxt[i];
-        if (k == 0) load_unit(t, 1, nxt); else if (tn <= t_end) load_unit(tn, 0, nxt);      // next unit's loads fly meanwhile
-        if (k == 0) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * xf.idx, xf.phase ^ 1, 8));
-        const int c8 = c8_0 + k;
-        float ca[8], cbv[8];
+        for (int half = 0; half < 2; ++half) {                    // slots [0, 192) then [192, 360): 6 iterations each
+          uint4 raw[NIT / 2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { ca[j] = s_coef[c8 * 8 + j]; cbv[j] = s_coef[64 + c8 * 8 + j]; }
-        uint4* chunk = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes) + c8 * (TC_PH * TC_PW);
+          for (int i = 0; i < NIT / 2; ++i) { const int idx = lane + 32 * (half * (NIT / 2) + i); if (idx < NSLOT) raw[i] = run[idx]; }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const int pos = lane + 32 * i;
-          if (pos < TC_PH * TC_PW) {
-            float f[8];
-            unpack8<T>(cur[i], f);
-            if (all_inside) {
+          for (int i = 0; i < NIT / 2; ++i) {
+            const int it = half * (NIT / 2) + i;
+            const int idx = lane + 32 * it;
+            if (idx < NSLOT) {
+              const bool ch1 = it > NPOS / 32 || (it == NPOS / 32 && second);
+              float f[8];
+              unpack8<T>(raw[i], f);
+              const bool inside = all_inside || ((inside_bits >> it) & 1u);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { const float z = fmaf(ca[j], f[j], cbv[j]); f[j] = fmaxf(z, 0.01f * z); }
-            } else {
-              const bool inside = (inside_bits >> i) & 1u;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { const float z = fmaf(ca[j], f[j], cbv[j]); f[j] = inside ? fmaxf(z, 0.01f * z) : 0.f; }
+              for (int j = 0; j < 8; ++j) {
+                const float ca = ch1 ? a1[j] : a0[j], cbv = ch1 ? b1[j] : b0[j];
+                const float z = fmaf(ca, f[j], cbv);
+                f[j] = inside ? fmaxf(z, 0.01f * z) : 0.f;
+              }
+              run[idx] = pack8<T>(f);
             }
-            chunk[pos] = pack8<T>(f);
           }
         }
+        DWMH_TIMED_WAIT(w1_, tc::fence_proxy_async());
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
+        xf.advance(SA);
       }
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
-      xf.advance(SA);
-      t = tn;
     }
   } else if (warp == 0) {
     // ---------------- activation producer: one TMA box per (input plane, channel chunk) -----------
@@ -474,15 +472,57 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         fresh.advance(R);
         ++next_fresh;
       }
-      if (plain && p.resident && zo_hi - zo_lo == 2 && lo_slot + 3 <= R && 3 * CB <= 256 && fresh_from == zo_hi) {
-        // ---- steady state (interior plane, slots contiguous, exactly output plane t+1 is new) ----
+      if (plain && zo_hi - zo_lo == 2 && R >= 3 && 3 * CB <= 256 && fresh_from == zo_hi) {
+        // ---- steady state (interior plane, exactly output plane t+1 is new).  The three accumulator slots are
+        // contiguous except at the ring wrap, where every MMA is issued as two (the general path is ~5x slower per MMA,
+        // and 2 of every R planes straddle the wrap).
         const uint32_t col = tmem + lo_slot * CB;
         const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17), id3 = idesc0 | (((3 * CB) >> 3) << 17);
+        const bool wrap = lo_slot + 3 > R, wrapA = lo_slot + 2 == R;          // wrapA: slots R-2, R-1 | 0    else: R-1 | 0, 1
+        const uint32_t idA = wrapA ? id2 : idesc1, idB = wrapA ? idesc1 : id2, offB = wrapA ? 2 * CB : CB;
+        const uint32_t col1 = (lo_slot + 1 == R) ? tmem : col + CB, col2 = wrapA ? tmem : tmem + CB;      // slots lo+1, lo+2 when wrapping
         for (int kc = 0; kc < p.nkc; ++kc) {
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
+          const long long tc_ = prof_on ? clock64() : 0;
           tc::tc_fence_after();
+          const long long td_ = prof_on ? clock64() : 0;
           { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }   // result consumed after the burst
-          if (leader) {
+          const long long tb_ = prof_on ? clock64() : 0;
+          if (prof_on) { w3_ += td_ - tc_; w4_ += tb_ - td_; }
+          if (!p.resident) {
+            // streamed weight tiles: one ring slot per tap, shared by the groups of the CTA
+            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+#pragma unroll
+            for (int sft = 0; sft < 9; ++sft) {
+              if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
+              tc::tc_fence_after();
+              const uint32_t b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+              { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
+              if (leader) {
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) {
+                  const uint64_t adesc = tc_desc(a_hi, a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4));
+                  const uint32_t b0 = b_lo0 + kk * kstep_b;
+                  const bool first = sft == 0 && kk == 0 && kc == 0;
+                  if (!wrap) {
+                    if (first) {
+                      tc::umma_f16(col, adesc, tc_desc(b_hi, b0), id2, 1u);
+                      tc::umma_f16(col + 2 * CB, adesc, tc_desc(b_hi, b0 + 2 * CB), idesc1, 0u);
+                    } else tc::umma_f16(col, adesc, tc_desc(b_hi, b0), id3, 1u);
+                  } else if (first) {
+                    tc::umma_f16(col, adesc, tc_desc(b_hi, b0), idesc1, 1u);
+                    tc::umma_f16(col1, adesc, tc_desc(b_hi, b0 + CB), idesc1, 1u);
+                    tc::umma_f16(col2, adesc, tc_desc(b_hi, b0 + 2 * CB), idesc1, 0u);
+                  } else {
+                    tc::umma_f16(col, adesc, tc_desc(b_hi, b0), idA, 1u);
+                    tc::umma_f16(tmem, adesc, tc_desc(b_hi, b0 + offB), idB, 1u);
+                  }
+                }
+              }
+              if (elected) tc::umma_commit(b_empty + 8 * b.idx);
+              b.advance(NB);
+            }
+          } else if (leader && !wrap) {
             const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
 #pragma unroll
@@ -499,7 +539,28 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               }
               bl += tile16;
             }
+          } else if (leader) {
+            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
+#pragma unroll
+            for (int sft = 0; sft < 9; ++sft) {
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                const uint64_t adesc = tc_desc(a_hi, a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4));
+                const uint32_t b0 = bl + kk * kstep_b;
+                if (sft == 0 && kk == 0 && kc == 0) {
+                  tc::umma_f16(col, adesc, tc_desc(b_hi, b0), idesc1, 1u);
+                  tc::umma_f16(col1, adesc, tc_desc(b_hi, b0 + CB), idesc1, 1u);
+                  tc::umma_f16(col2, adesc, tc_desc(b_hi, b0 + 2 * CB), idesc1, 0u);
+                } else {
+                  tc::umma_f16(col, adesc, tc_desc(b_hi, b0), idA, 1u);
+                  tc::umma_f16(tmem, adesc, tc_desc(b_hi, b0 + offB), idB, 1u);
+                }
+              }
+              bl += tile16;
+            }
           }
+          if (prof_on) w2_ += clock64() - tb_;
           if (elected) tc::umma_commit(a_empty + 8 * a.idx);
           a.advance(SA);
         }
@@ -660,19 +721,28 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       for (int t = z_lo; t < z_end; ++t) {
         DWMH_TIMED_WAIT(w0_, tc::mbar_wait(acc_full + 8 * slot, phase, 7));
         tc::tc_fence_after();
-        for (int ch = 0; ch < nch; ++ch) {
-          uint32_t r[16];
-          tc::tmem_ld16(tm_lane + slot * CB + ch * 16, r);
+        // two 16-column chunks per TMEM wait; the (parity, channel offset) of a chunk advances incrementally (no divisions)
+        int cofs = 0, qa = 0, qb = 0, qw = 0;
+        for (int ch = 0; ch < nch; ch += 2) {
+          uint32_t r[2][16];
+          tc::tmem_ld16(tm_lane + slot * CB + ch * 16, r[0]);
+          tc::tmem_ld16(tm_lane + slot * CB + ch * 16 + 16, r[1]);
           tc::tmem_ld_wait();
-          float a[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(r[i]);
-          const int col = ch * 16, qc = col / p.CBt, cofs = col - qc * p.CBt;
-          const int qa = qc / (p.osh * p.osw), qb = (qc / p.osw) % p.osh, qw = qc % p.osw;
-          if (valid) {
-            uint4* o = out_n + (size_t)((cb * p.CBt + cofs) >> 3) * Vo + ((size_t)(t * p.osd + qa) * Ho + (h * p.osh + qb)) * Wo + (w * p.osw + qw);
-            o[0] = pack8<T>(a);
-            o[Vo] = pack8<T>(a + 8);
+          for (int u = 0; u < 2; ++u) {
+            float a[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(r[u][i]);
+            if (valid) {
+              uint4* o = out_n + (size_t)((cb * p.CBt + cofs) >> 3) * Vo + ((size_t)(t * p.osd + qa) * Ho + (h * p.osh + qb)) * Wo + (w * p.osw + qw);
+              o[0] = pack8<T>(a);
+              o[Vo] = pack8<T>(a + 8);
+            }
+            cofs += 16;
+            if (cofs == p.CBt) {
+              cofs = 0;
+              if (++qw == p.osw) { qw = 0; if (++qb == p.osh) { qb = 0; ++qa; } }
+            }
           }
         }
         tc::tc_fence_before();
@@ -779,6 +849,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     atomicAdd(p.prof + role * 4 + 0, (unsigned long long)w0_);
     atomicAdd(p.prof + role * 4 + 1, (unsigned long long)w1_);
     atomicAdd(p.prof + role * 4 + 2, (unsigned long long)(clock64() - tstart_));
+    atomicAdd(p.prof + role * 4 + 3, (unsigned long long)w2_);
+    if (role == 1) { atomicAdd(p.prof + 3, (unsigned long long)w3_); atomicAdd(p.prof + 11, (unsigned long long)w4_); }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -972,7 +1044,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   kp.ncb = cout / CB; kp.SA = SA; kp.NB = NB; kp.resident = resident; kp.G = G;
   kp.xf_src = nullptr;
   kp.xform = 0; kp.xf_sums = nullptr; kp.xf_gamma = nullptr; kp.xf_beta = nullptr; kp.xf_inv_count = 0.f;
-  t.xform_ok = !strided && resident && c1 == 0 && KC == 32 && cin == 32 && CB <= 32 && SA >= 3;
+  t.xform_ok = !strided && resident && c1 == 0 && KC == 32 && (cin == 32 || cin == 64) && CB <= 32 && SA >= 3;
   kp.R = std::min(TC_MAX_R, (512 / G) / CB);
   kp.fmt = bf16 ? 1 : 0;
   kp.a_stage_bytes = KC * 360; kp.b_tile_bytes = kp.jmax * CB * KC * 2;
@@ -1030,6 +1102,7 @@ inline int tc_prepare_tconv(TcLayer& t, const std::vector<float>& w, int cin, in
   kp.nclass = 1; kp.Jlo = 0; kp.Jhi = 0; kp.jmax = 1; kp.tiles_per_kc = 1; kp.Din = in_sp[0];
   kp.cls[0] = TcClassDesc{1 << 4, 0, 1, 0};
   const int CB = nco * CBt;
+  if (CB % 32) return 0;                 // the scatter epilogue reads two 16-column chunks per step
   int KC = 64;
   while (KC > 16 && cin % KC) KC >>= 1;
   const int budget = TC_SMEM_MAX - TC_SMEM_RESERVED;
@@ -1185,7 +1258,7 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
 #define DWMH_TC_LAUNCH_K(S, C, D) do { if (ks == 1) DWMH_TC_LAUNCH(1, S, C, D); else if (ks == 2) DWMH_TC_LAUNCH(2, S, C, D); else DWMH_TC_LAUNCH(4, S, C, D); } while (0)
   if (kp.first) conv3_tc_kernel<T, 2, true, false, true, false, true><<<grid, 512, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
   else if (kp.xform) {
-    const unsigned xthreads = TC_THREADS * kp.G;
+    const unsigned xthreads = (TC_THREADS + 32) * kp.G;
     if (kp.G == 2) conv3_tc_kernel<T, 2, true, false, true, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
     else conv3_tc_kernel<T, 2, true, false, false, true><<<grid, xthreads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
   } else if (kp.tconv) DWMH_TC_LAUNCH_K(false, true, false);
@@ -1200,8 +1273,8 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
     cudaStreamSynchronize(st);
     cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost);
     const double g = (double)grid;
-    fprintf(stderr, "tcprof C0=%d C1=%d Cout=%d CB=%d KC=%d D=%d res=%d grid=%u planes/cta=%d | act-prod wait_empty %.0f w1 %.0f tot %.0f | mma wait_a %.0f wait_acc/b %.0f tot %.0f | epi wait_full %.0f tot %.0f | w-prod wait %.0f tot %.0f (cycles per CTA)\n",
-            kp.C0, kp.C1, kp.Cout, kp.CB, kp.KC, kp.D, kp.resident, grid, kp.ZB, h[0] / g, h[1] / g, h[2] / g, h[4] / g, h[5] / g, h[6] / g, h[8] / g, h[10] / g, h[12] / g, h[14] / g);
+    fprintf(stderr, "tcprof C0=%d C1=%d Cout=%d CB=%d KC=%d D=%d res=%d grid=%u planes/cta=%d | act-prod wait_empty %.0f w1 %.0f tot %.0f | mma wait_a %.0f wait_acc/b %.0f burst %.0f fence %.0f peek %.0f tot %.0f | epi wait_full %.0f tot %.0f | w-prod wait %.0f tot %.0f (cycles per CTA)\n",
+            kp.C0, kp.C1, kp.Cout, kp.CB, kp.KC, kp.D, kp.resident, grid, kp.ZB, h[0] / g, h[1] / g, h[2] / g, h[4] / g, h[5] / g, h[7] / g, h[3] / g, h[11] / g, h[6] / g, h[8] / g, h[10] / g, h[12] / g, h[14] / g);
   }
   return 0;
 }
