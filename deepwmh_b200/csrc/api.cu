@@ -688,8 +688,8 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
       st = st_aux;
       NormParams np{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
       const int64_t V = L.vout();
-      const int gx = (int)std::min<int64_t>((V + 255) / 256, 1024);
-      dim3 grid(gx, nb * (L.cout >> 3));
+      const int gx = (int)std::min<int64_t>((V / 2 + 255) / 256, 1024);      // a thread handles voxel pairs (256-bit accesses)
+      dim3 grid(std::max(gx, 1), nb * (L.cout >> 3));
       S2dParams sp{L.s2d, L.out_sp[0], L.out_sp[1], L.out_sp[2], L.s2d_s[0], L.s2d_s[1], L.s2d_s[2]};
       instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, np, L.cout, V, sp);
       c->launches++;

@@ -171,7 +171,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem + (uint32_t)g * 256u;       // group 1 owns TMEM columns 256..511
   const bool prof_on = (p.dbg & 8) != 0;
-  long long w0_ = 0, w1_ = 0, w2_ = 0, w3_ = 0, w4_ = 0;
+  long long w0_ = 0, w1_ = 0, w2_ = 0, w3_ = 0;      // profiling (dbg & 8): barrier waits, issue bursts, general-path time
   const long long tstart_ = clock64();
 
   if (idle) {
@@ -483,12 +483,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const uint32_t col1 = (lo_slot + 1 == R) ? tmem : col + CB, col2 = wrapA ? tmem : tmem + CB;      // slots lo+1, lo+2 when wrapping
         for (int kc = 0; kc < p.nkc; ++kc) {
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
-          const long long tc_ = prof_on ? clock64() : 0;
           tc::tc_fence_after();
-          const long long td_ = prof_on ? clock64() : 0;
           { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }   // result consumed after the burst
           const long long tb_ = prof_on ? clock64() : 0;
-          if (prof_on) { w3_ += td_ - tc_; w4_ += tb_ - td_; }
           if (!p.resident) {
             // streamed weight tiles: one ring slot per tap, shared by the groups of the CTA
             const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
@@ -627,6 +624,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         continue;
       }
       // ---- general path: parity classes, ring wrap, block edges, streamed weights -------------------
+      const long long tg_ = prof_on ? clock64() : 0;
       bool first_mma = true;
       for (int c = 0; c < p.nclass; ++c) {
         const int dlo = max(t + p.cls[c].jlo, z_lo), dhi = min(t + p.cls[c].jlo + p.cls[c].jcnt - 1, z_end - 1);
@@ -701,6 +699,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         ++next_done;
       }
       __syncwarp();
+      if (prof_on) w3_ += clock64() - tg_;
     }
     }   // !FIRST
   } else {
@@ -850,7 +849,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     atomicAdd(p.prof + role * 4 + 1, (unsigned long long)w1_);
     atomicAdd(p.prof + role * 4 + 2, (unsigned long long)(clock64() - tstart_));
     atomicAdd(p.prof + role * 4 + 3, (unsigned long long)w2_);
-    if (role == 1) { atomicAdd(p.prof + 3, (unsigned long long)w3_); atomicAdd(p.prof + 11, (unsigned long long)w4_); }
+    if (role == 1) atomicAdd(p.prof + 3, (unsigned long long)w3_);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -1273,8 +1272,8 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
     cudaStreamSynchronize(st);
     cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost);
     const double g = (double)grid;
-    fprintf(stderr, "tcprof C0=%d C1=%d Cout=%d CB=%d KC=%d D=%d res=%d grid=%u planes/cta=%d | act-prod wait_empty %.0f w1 %.0f tot %.0f | mma wait_a %.0f wait_acc/b %.0f burst %.0f fence %.0f peek %.0f tot %.0f | epi wait_full %.0f tot %.0f | w-prod wait %.0f tot %.0f (cycles per CTA)\n",
-            kp.C0, kp.C1, kp.Cout, kp.CB, kp.KC, kp.D, kp.resident, grid, kp.ZB, h[0] / g, h[1] / g, h[2] / g, h[4] / g, h[5] / g, h[7] / g, h[3] / g, h[11] / g, h[6] / g, h[8] / g, h[10] / g, h[12] / g, h[14] / g);
+    fprintf(stderr, "tcprof C0=%d C1=%d Cout=%d CB=%d KC=%d D=%d res=%d grid=%u planes/cta=%d | act-prod wait_empty %.0f w1 %.0f tot %.0f | mma wait_a %.0f wait_acc/b %.0f burst %.0f general-path %.0f tot %.0f | epi wait_full %.0f tot %.0f | w-prod wait %.0f tot %.0f (cycles per CTA)\n",
+            kp.C0, kp.C1, kp.Cout, kp.CB, kp.KC, kp.D, kp.resident, grid, kp.ZB, h[0] / g, h[1] / g, h[2] / g, h[4] / g, h[5] / g, h[7] / g, h[3] / g, h[6] / g, h[8] / g, h[10] / g, h[12] / g, h[14] / g);
   }
   return 0;
 }

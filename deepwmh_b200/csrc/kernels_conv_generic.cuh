@@ -357,6 +357,17 @@ __global__ void __launch_bounds__(128) conv_generic_kernel(ConvParams p) {
 // s2d[n][class][C/8][D/sd][H/sh][W/sw][8] with class order tc_s2d_class().
 struct S2dParams { void* dst; int D, H, W, sd, sh, sw; };
 
+// 256-bit global accesses (sm_100): two 16-byte voxel-chunks per instruction keep twice the bytes in flight per thread;
+// the pass is a pure stream and was bound by memory-level parallelism (2048 threads x 16 B per SM).
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) instnorm_lrelu_kernel(const void* __restrict__ raw, int raw32, void* __restrict__ y, NormParams np,
                                                              int C, int64_t V, S2dParams sp) {
@@ -374,6 +385,42 @@ __global__ void __launch_bounds__(256) instnorm_lrelu_kernel(const void* __restr
   const int Ds = sp.D / sp.sd, Hs = sp.H / sp.sh, Ws = sp.W / sp.sw;
   const int64_t Vs = (int64_t)Ds * Hs * Ws;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  auto s2d_store = [&](int64_t v, const uint4& o) {
+    const int w = (int)(v % sp.W), h = (int)((v / sp.W) % sp.H), d = (int)(v / ((int64_t)sp.W * sp.H));
+    const int c = tc_s2d_class(d, h, w, sp.sd, sp.sh, sp.sw);
+    const int64_t vs = ((int64_t)(d / sp.sd) * Hs + (h / sp.sh)) * Ws + (w / sp.sw);
+    reinterpret_cast<uint4*>(sp.dst)[(((size_t)n * nclass + c) * (C >> 3) + cc) * Vs + vs] = o;
+  };
+  if ((V & 1) == 0) {
+    // voxel pairs: one 256-bit load (fp16 raw) or two (fp32 raw), one 256-bit store
+    const int64_t V2 = V >> 1;
+    for (int64_t v2 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v2 < V2; v2 += stride) {
+      float f[2][8];
+      if (raw32) {
+        uint4 q0, q1, q2, q3;
+        ld_global_256(rrow32 + 4 * v2, q0, q1);
+        ld_global_256(rrow32 + 4 * v2 + 2, q2, q3);
+        const uint4 q[4] = {q0, q1, q2, q3};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          f[e][0] = __uint_as_float(q[2 * e].x); f[e][1] = __uint_as_float(q[2 * e].y); f[e][2] = __uint_as_float(q[2 * e].z); f[e][3] = __uint_as_float(q[2 * e].w);
+          f[e][4] = __uint_as_float(q[2 * e + 1].x); f[e][5] = __uint_as_float(q[2 * e + 1].y); f[e][6] = __uint_as_float(q[2 * e + 1].z); f[e][7] = __uint_as_float(q[2 * e + 1].w);
+        }
+      } else {
+        uint4 q0, q1;
+        ld_global_256(rrow + 2 * v2, q0, q1);
+        unpack8<T>(q0, f[0]); unpack8<T>(q1, f[1]);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[e][j] = lrelu(fmaf(a[j], f[e][j], b[j]));
+      const uint4 o0 = pack8<T>(f[0]), o1 = pack8<T>(f[1]);
+      st_global_256(row + 2 * v2, o0, o1);
+      if (sp.dst) { s2d_store(2 * v2, o0); s2d_store(2 * v2 + 1, o1); }
+    }
+    return;
+  }
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride) {
     float f[8];
     if (raw32) {
@@ -384,12 +431,7 @@ __global__ void __launch_bounds__(256) instnorm_lrelu_kernel(const void* __restr
     for (int j = 0; j < 8; ++j) f[j] = lrelu(fmaf(a[j], f[j], b[j]));
     const uint4 o = pack8<T>(f);
     row[v] = o;
-    if (sp.dst) {
-      const int w = (int)(v % sp.W), h = (int)((v / sp.W) % sp.H), d = (int)(v / ((int64_t)sp.W * sp.H));
-      const int c = tc_s2d_class(d, h, w, sp.sd, sp.sh, sp.sw);
-      const int64_t vs = ((int64_t)(d / sp.sd) * Hs + (h / sp.sh)) * Ws + (w / sp.sw);
-      reinterpret_cast<uint4*>(sp.dst)[(((size_t)n * nclass + c) * (C >> 3) + cc) * Vs + vs] = o;
-    }
+    if (sp.dst) s2d_store(v, o);
   }
 }
 
