@@ -42,7 +42,9 @@ constexpr int TC_PLANE_BYTES = TC_PH * TC_PW * 16;     // one 8-channel chunk of
 constexpr int TC_MAX_SA = 4, TC_MAX_NB = 40, TC_MAX_R = 16;
 constexpr int TC_SMEM_MAX = 232448;                    // 227 KB opt-in limit
 constexpr int TC_SMEM_RESERVED = 5120;                 // barriers + TMEM pointer + statistics
-constexpr int TC_SMEM_RESERVED_FIRST = 8192;           // FIRST kernels: + two rolling 3-slice input windows
+constexpr int TC_SMEM_RESERVED_FIRST = 10240;          // FIRST kernels: + two 4-slot rings of haloed input slices
+constexpr int TC_FIRST_PITCH = 12;                     // words per ring row (10 used): 2 rows apart = 24 words -> conflict-free LDS
+constexpr int TC_FIRST_SLICE = TC_PH * TC_FIRST_PITCH;
 constexpr int TC_FIRST_STAGE_BYTES = 8 * 128 * 16;     // im2col operand of one output plane: 4 hi + 4 lo chunks of 8 taps
 
 // One parity class of a strided conv (a plain stride-1 conv has exactly one class).  The producer tensor of
@@ -130,7 +132,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * nbar * p.G);
   float* s_stat = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)g * 2 * CB;   // [2][CB] per group
   float* s_coef = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)g * 2 * 64;   // XFORM: a[64], b[64]
-  float* s_slice = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)p.G * 2 * 64 + (size_t)g * 4 * TC_PH * TC_PW;   // FIRST: 4-slot ring of haloed input slices
+  float* s_slice = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)p.G * 2 * 64 + (size_t)g * 4 * TC_FIRST_SLICE;   // FIRST: 4-slot ring of haloed input slices
   const uint32_t smem_a = smem_base + (uint32_t)g * SA * p.a_stage_bytes;          // this group's activation ring
   const uint32_t s_full = smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + (uint32_t)g * 64u, s_empty = s_full + 32u;   // FIRST: slice ring barriers
 
@@ -214,11 +216,12 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     };
     auto step = [&](int k, float (&v)[6]) {
       if (k >= 4) tc::mbar_wait(s_empty + 8 * (k & 3), ((k >> 2) & 1) ^ 1, 10);
-      uint32_t* dst = ring + (k & 3) * (TC_PH * TC_PW);
+      uint32_t* dst = ring + (k & 3) * TC_FIRST_SLICE;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         const float hf = __uint_as_float(__float_as_uint(v[i]) & kHiMask);
-        if (lane + 32 * i < TC_PH * TC_PW) dst[lane + 32 * i] = ActT<T>::from_f2(hf, v[i] - hf);
+        const int pos = lane + 32 * i, r = pos / TC_PW;
+        if (pos < TC_PH * TC_PW) dst[r * TC_FIRST_PITCH + (pos - r * TC_PW)] = ActT<T>::from_f2(hf, v[i] - hf);
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(s_full + 8 * (k & 3));
@@ -251,11 +254,19 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       DWMH_TIMED_WAIT(w1_, tc::mbar_wait(s_full + 8 * ((j + 2) & 3), ((j + 2) >> 2) & 1, 11));
       tc::mbar_wait(a_empty + 8 * xf.idx, xf.phase ^ 1, 9);
       uint4* stage = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes);
-      const uint32_t* sl[3] = {ring + (j & 3) * (TC_PH * TC_PW), ring + ((j + 1) & 3) * (TC_PH * TC_PW), ring + ((j + 2) & 3) * (TC_PH * TC_PW)};
+      const uint32_t* sl[3] = {ring + (j & 3) * TC_FIRST_SLICE, ring + ((j + 1) & 3) * TC_FIRST_SLICE, ring + ((j + 2) & 3) * TC_FIRST_SLICE};
+      // a lane builds two vertically adjacent rows (hh, ww), (hh + 1, ww): they share 2 of their 3 input rows
+      const int hh = (l64 >> 3) * 2, ww = l64 & 7;
+      uint32_t val[3][4][3];
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) val[dz][r][kw] = sl[dz][(hh + r) * TC_FIRST_PITCH + ww + kw];
 #pragma unroll
       for (int rr = 0; rr < 2; ++rr) {
-        const int m = l64 + 64 * rr;
-        const int hh = m >> 3, ww = m & 7;
+        const int m = (hh + rr) * 8 + ww;
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
@@ -263,10 +274,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int tap = 2 * q + e;
-            if (tap < 27) {
-              const int dz = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-              x[e] = sl[dz][(hh + kh) * TC_PW + (ww + kw)];
-            } else x[e] = 0u;
+            x[e] = tap < 27 ? val[tap / 9][(tap / 3) % 3 + rr][tap % 3] : 0u;
           }
           hi[q] = __byte_perm(x[0], x[1], 0x5410);
           lo[q] = __byte_perm(x[0], x[1], 0x7632);
@@ -277,7 +285,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           stage[(4 + c) * 128 + m] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
         }
       }
-      DWMH_TIMED_WAIT(w0_, tc::fence_proxy_async());
+      tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) { tc::mbar_arrive(a_ready + 8 * xf.idx); tc::mbar_arrive(s_empty + 8 * (j & 3)); }
       xf.advance(SA);

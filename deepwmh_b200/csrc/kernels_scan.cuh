@@ -108,6 +108,23 @@ __global__ void __launch_bounds__(256) head_softmax_kernel(const T* __restrict__
   if (v >= V) return;
   const uint4* yp = reinterpret_cast<const uint4*>(y) + (size_t)n * (C >> 3) * V + v;
   float l0 = 0.f, l1 = 0.f;
+  if (C == 32) {          // the usual head: all four channel chunks in flight before the first use
+    uint4 q[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) q[cc] = ld_stream(yp + (size_t)cc * V);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      float f[8];
+      unpack8<T>(q[cc], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cc * 8 + j;
+        const float x = np.sums ? lrelu(fmaf(sa[c], f[j], sb[c])) : f[j];
+        l0 = fmaf(w0[c], x, l0);
+        l1 = fmaf(w1[c], x, l1);
+      }
+    }
+  } else
   for (int cc = 0; cc < (C >> 3); ++cc) {
     float f[8];
     unpack8<T>(ld_stream(yp + (size_t)cc * V), f);
