@@ -122,6 +122,42 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def conv_algorithmic_bytes(plans, raw32_max_edge=64):
+    """Bytes every conv / transposed-conv launch of ONE tile-forward must move at least once: input activations
+    (fp16; fp32 for the 1-channel input volume), output (fp16 raw, fp32 for layers whose output edge <= raw32_max_edge)
+    and the layer's fp16 weights.  Returns (total bytes, number of launches)."""
+    import numpy as np
+    st = plans["plans_per_stage"][max(plans["plans_per_stage"].keys())]
+    pools, kers = st["pool_op_kernel_sizes"], st["conv_kernel_sizes"]
+    shape = np.array(st["patch_size"], dtype=np.int64)
+    feats = [plans["base_num_features"]]
+    for _ in pools:
+        feats.append(min(int(round(feats[-1] * 2)), 320))
+    total, launches, cin, shapes = 0, 0, plans["num_modalities"], []
+    in_shape = shape.copy()
+
+    def out_bytes(c, sp, last=False):
+        return int(np.prod(sp)) * c * (4 if (max(sp) <= raw32_max_edge and not last) else 2)
+    for d in range(len(pools) + 1):
+        if d > 0:
+            shape = shape // np.array(pools[d - 1])
+        k = int(np.prod(kers[d]))
+        total += int(np.prod(in_shape)) * cin * (4 if d == 0 else 2) + out_bytes(feats[d], shape) + cin * feats[d] * k * 2
+        total += int(np.prod(shape)) * feats[d] * 2 + out_bytes(feats[d], shape) + feats[d] * feats[d] * k * 2
+        launches += 2
+        cin, in_shape = feats[d], shape.copy()
+        shapes.append(shape.copy())
+    for u in range(len(pools)):
+        skip, sp = feats[-(2 + u)], shapes[-(2 + u)]
+        k = int(np.prod(kers[-(u + 1)]))
+        total += int(np.prod(in_shape)) * cin * 2 + int(np.prod(sp)) * skip * 2 + cin * skip * int(np.prod(pools[-(u + 1)])) * 2      # transposed conv
+        total += int(np.prod(sp)) * 2 * skip * 2 + out_bytes(skip, sp) + 2 * skip * skip * k * 2
+        total += int(np.prod(sp)) * skip * 2 + out_bytes(skip, sp, last=(u == len(pools) - 1)) + skip * skip * k * 2
+        launches += 3
+        cin, in_shape = skip, sp.copy()
+    return total, launches
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -245,6 +281,18 @@ def run_b200(args):
         cpu = {"value": 1.0 / (per * N_TILES * N_MIRRORS), "unit": "volumes/s", "cores": cores, "kind": "port",
                "sample": "%d of the 96 tile-forwards (128^3, softmax, x Gaussian/8) of the workload, fp32 oracle (torch CPU, %d threads), %.1f s per forward; volumes/s = 1/(96 x s per forward)" % (len(cpu_t), cores, per)}
     kinds = [n.layer_kernel_kind(i) for i in range(n.num_layers())]
+    # DRAM traffic per conv3_tc_kernel launch: not measurable inside a timed run; taken from the committed ncu pass
+    # (profiles/dram_traffic_r01.json, written by tools/dram_traffic.py from an ncu metrics run of the same 32-forward batch)
+    ab, nl = conv_algorithmic_bytes(plans)
+    alg_bytes = ab * args.max_batch / nl          # mean over the conv launches of one max_batch-forward batch
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic_r01.json")
+    if os.path.isfile(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = tj["tc_dram_bytes_per_launch"], "profiles/dram_traffic_r01.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d conv3_tc_kernel launches of one 32-forward batch)" % tj["tc_launches"]
+        except Exception:
+            traffic = None
     out = {
         "metric": "volumes/sec", "value": vps, "unit": "volumes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -255,7 +303,7 @@ def run_b200(args):
                    "l2": "192 MiB flush buffer written between steps; per-batch activation working set (~7 GB) >> 126 MB L2",
                    "tcgen05_layers": int(sum(kinds)), "direct_layers": int(len(kinds) - sum(kinds))},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": achieved / pk["tensor"],
-                     "traffic": None, "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM conv3d / strided conv / transposed conv)",
+                     "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel": "conv3_tc_kernel (tcgen05 implicit-GEMM conv3d / strided conv / transposed conv)",
                      "launches_per_volume": tc_launches, "avg_launch_ms": tc_ms / max(tc_launches, 1), "tflop_per_volume_in_kernel": tc_tflop,
                      "kernel_ms_per_volume": tc_ms, "kernel_share_of_step": tc_ms / (ms_dev / args.steps),
                      "conv_stack_ms_per_volume": conv_ms, "conv_stack_tflops": tflop_vol / (conv_ms / 1e3), "aggregate_ms_per_volume": agg_ms,
