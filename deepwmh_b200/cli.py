@@ -3,7 +3,7 @@
 
 Same flags (-i -n -m -o -g --skip-bfc --custom-task-name), same output tree
 (<out>/001_Preprocessed_Images/<case>_0000.nii.gz, <out>/002_Segmentations/{001_raw,002_postproc_3mm,003_postproc_fov}),
-same fail-fast behaviour (any error -> non-zero exit).  Additive: --gpus a,b,... shards the cases over GPUs
+same fail-fast behaviour (any error -> non-zero exit); the 3 mm spark removal (predict.py:158-163) runs on the device.  Additive: --gpus a,b,... shards the cases over GPUs
 (one worker process per GPU, no collective).  Out of scope and therefore external, exactly as in the reference:
 N4 bias-field correction (ANTs binary; use --skip-bfc or have N4BiasFieldCorrection on PATH), ROBEX FOV masking
 (skipped with a notice unless ROBEX_DIR is set) and GIF previews.
@@ -72,7 +72,7 @@ def _check_cases(case_names: List[str], images: List[str]):
             sys.exit(1)
 
 
-def predict_case(trainer, plans: Dict, in_file: str, out_file: str, softmax_file: str = None):
+def predict_case(trainer, plans: Dict, in_file: str, out_file: str, softmax_file: str = None, post3mm_file: str = None):
     """One case through crop -> z-score -> tiled prediction -> paste back, the way nnUNet_predict does for a single
     modality."""
     import torch
@@ -99,21 +99,25 @@ def predict_case(trainer, plans: Dict, in_file: str, out_file: str, softmax_file
     seg_pred = seg_pred.transpose(tb)
     full = preprocess.paste_back(seg_pred.astype(np.uint8), data.shape[1:], bbox)
     nifti.write_nifti(out_file, np.transpose(full, (2, 1, 0)), hdr, dtype=np.uint8)
+    if post3mm_file is not None:                                                   # predict.py:158-163, on the device
+        with torch.cuda.device(net.device):
+            clean = net.remove_3mm_sparks(torch.from_numpy(full).to(net.device), list(hdr["spacing"])).cpu().numpy()
+        nifti.write_nifti(post3mm_file, np.transpose(clean, (2, 1, 0)).astype(np.float32), hdr, dtype=np.float32)
     if softmax_file is not None:                                                   # the fork's --save_softmax: background channel
         bg = np.ones(data.shape[1:], dtype=np.float32)
         bg[tuple(slice(b[0], b[1]) for b in bbox)] = softmax[0].transpose(tb)
         nifti.write_nifti(softmax_file, np.transpose(bg, (2, 1, 0)), hdr, dtype=np.float32)
 
 
-def _worker(gpu: int, cases: List[Tuple[str, str, str]], model: Dict[str, str]):
+def _worker(gpu: int, cases: List[Tuple[str, str, str, str]], model: Dict[str, str]):
     import torch
     import deepwmh_b200
     plans = load_plans(model["plans"])
     trainer = deepwmh_b200.nnUNetTrainerV2(plans, device=gpu, max_batch=32)
     ckpt = torch.load(model["checkpoint"], map_location="cpu", weights_only=False)
     trainer.load_checkpoint_ram(ckpt, False)
-    for case, src, dst in cases:
-        predict_case(trainer, plans, src, dst)
+    for case, src, dst, post in cases:
+        predict_case(trainer, plans, src, dst, post3mm_file=post)
         print("predicted %s" % case)
     trainer.network.close()
 
@@ -166,7 +170,8 @@ def main(argv=None):
             if rc != 0:
                 raise RuntimeError("N4BiasFieldCorrection failed with exit code %d" % rc)
 
-    work = [(c, os.path.join(image_folder, "%s_0000.nii.gz" % c), os.path.join(raw_seg, "%s.nii.gz" % c)) for c in args.case_names]
+    work = [(c, os.path.join(image_folder, "%s_0000.nii.gz" % c), os.path.join(raw_seg, "%s.nii.gz" % c),
+             os.path.join(post_3mm, "%s.nii.gz" % c)) for c in args.case_names]
     gpus = [int(g) for g in args.gpus.split(",")] if args.gpus else [args.gpu]
     if len(gpus) == 1:
         _worker(gpus[0], work, model)
@@ -186,10 +191,9 @@ def main(argv=None):
             if p.exitcode != 0:
                 raise RuntimeError("prediction worker failed with exit code %s" % p.exitcode)
 
-    for case, _, seg_path in work:                                             # predict.py:158-163
-        seg, hdr = nifti.read_nifti(seg_path)
-        clean = preprocess.remove_3mm_sparks(seg, list(hdr["spacing"]))
-        nifti.write_nifti(os.path.join(post_3mm, "%s.nii.gz" % case), clean.astype(np.float32), hdr, dtype=np.float32)
+    for case, _, seg_path, post_path in work:                                  # predict.py:158-163 ran inside the workers
+        if not (os.path.isfile(seg_path) and os.path.isfile(post_path)):
+            raise RuntimeError('prediction of case "%s" did not produce its outputs.' % case)
     if os.environ.get("ROBEX_DIR"):
         print("** ROBEX FOV masking is an external program (predict.py:165-181) and is not run by this entry point.")
     print("")

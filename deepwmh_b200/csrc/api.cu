@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "kernels_scan.cuh"
+#include "kernels_ccl.cuh"
 #include "kernels_conv_generic.cuh"
 #include "conv_tcgen05.cuh"
 
@@ -105,6 +106,7 @@ struct dwmh_ctx {
   float* gauss_dev = nullptr; std::vector<float> gauss_host; bool gauss_custom = false;
   SampleMeta* metas_dev = nullptr; size_t metas_cap = 0;
   double* zs_acc = nullptr;
+  int* ccl_labels = nullptr; int* ccl_sizes = nullptr; size_t ccl_cap_l = 0, ccl_cap_s = 0;   // dwmh_remove_sparks workspace
   // host-buffer path (grow only)
   float* hv_vol = nullptr; float* hv_pad = nullptr; float* hv_agg = nullptr; float* hv_wgt = nullptr; uint8_t* hv_seg = nullptr;
   size_t hv_vol_cap = 0, hv_pad_cap = 0, hv_agg_cap = 0, hv_wgt_cap = 0, hv_seg_cap = 0;
@@ -231,6 +233,7 @@ extern "C" int dwmh_destroy(dwmh_ctx* c) {
   for (auto& L : c->layers) { free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc); }
   free_dev(c->w_head_dev); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
   free_dev(c->hv_vol); free_dev(c->hv_pad); free_dev(c->hv_agg); free_dev(c->hv_wgt); free_dev(c->hv_seg);
+  free_dev(c->ccl_labels); free_dev(c->ccl_sizes);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (auto e : c->tcev) cudaEventDestroy(e);
   delete c;
@@ -896,6 +899,27 @@ static int grow(V** p, size_t* cap, size_t need) {
   *p = nullptr; *cap = 0;
   CU_TRY(cudaMalloc((void**)p, need * sizeof(V)));
   *cap = need;
+  return 0;
+}
+
+// remove_sparks (deepwmh/analysis/image_ops.py:325-344) on the device; seg and out may alias.
+extern "C" int dwmh_remove_sparks(dwmh_ctx* c, const uint8_t* seg, int32_t X, int32_t Y, int32_t Z, int32_t min_volume,
+                                  uint8_t* out, void* stream_) {
+  if (!c || !seg || !out) return fail("dwmh_remove_sparks: null argument");
+  if (X <= 0 || Y <= 0 || Z <= 0) return fail("dwmh_remove_sparks: empty volume");
+  const int64_t V = (int64_t)X * Y * Z;
+  if (V >= (int64_t)1 << 31) return fail("dwmh_remove_sparks: volume of %lld voxels exceeds the 32-bit label range", (long long)V);
+  CU_TRY(cudaSetDevice(c->device));
+  DW_TRY(grow(&c->ccl_labels, &c->ccl_cap_l, (size_t)V));
+  DW_TRY(grow(&c->ccl_sizes, &c->ccl_cap_s, (size_t)V));
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int grid = c->num_sms * 8;
+  ccl_init_kernel<<<grid, 256, 0, st>>>(seg, c->ccl_labels, c->ccl_sizes, V);
+  ccl_merge_kernel<<<grid, 256, 0, st>>>(c->ccl_labels, X, Y, Z);
+  ccl_count_kernel<<<grid, 256, 0, st>>>(c->ccl_labels, c->ccl_sizes, V);
+  ccl_filter_kernel<<<grid, 256, 0, st>>>(c->ccl_labels, c->ccl_sizes, out, min_volume, V);
+  c->launches += 4;
+  CU_TRY(cudaGetLastError());
   return 0;
 }
 

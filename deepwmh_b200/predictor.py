@@ -160,6 +160,23 @@ class SegmentationNetwork:
         check(self._lib.dwmh_finalize(self._ctx, _ptr(agg), _ptr(wgt), _ptr(agg), _ptr(seg), X, Y, Z, _stream()))
         return seg, agg
 
+    def remove_sparks(self, seg: torch.Tensor, min_volume: int = 3) -> torch.Tensor:
+        """`remove_sparks` (deepwmh/analysis/image_ops.py:325-344) on the device: uint8 label map [X,Y,Z] -> uint8 mask of the
+        6-connected components with at least min_volume voxels."""
+        assert seg.is_cuda and seg.dtype == torch.uint8 and seg.is_contiguous() and seg.dim() == 3
+        out = torch.empty_like(seg)
+        X, Y, Z = seg.shape
+        check(self._lib.dwmh_remove_sparks(self._ctx, _ptr(seg), X, Y, Z, int(min_volume), _ptr(out), _stream()))
+        return out
+
+    def remove_3mm_sparks(self, seg: torch.Tensor, voxel_size: Sequence[float]) -> torch.Tensor:
+        """`remove_3mm_sparks` (image_ops.py:346-367): the voxel-size rule on the host, the component filter on the device."""
+        vs = [float(v) for v in voxel_size]
+        if max(vs) / min(vs) > 3.0:
+            return self.remove_sparks(seg, 3)
+        import numpy as _np
+        return self.remove_sparks(seg, max(int(_np.around(3.0 / (vs[0] * vs[1] * vs[2]))), 2))
+
     def num_tiles(self, shape: Sequence[int], step_size: float) -> int:
         s = _lib.compute_steps(self.patch_size, shape, step_size)
         return len(s[0]) * len(s[1]) * len(s[2])

@@ -99,6 +99,13 @@ int dwmh_finalize(dwmh_ctx* ctx, const float* agg_dev, const float* wgt_dev, flo
 int dwmh_axpy(dwmh_ctx* ctx, float* acc_dev, const float* x_dev, float alpha, int64_t n, void* stream);
 int dwmh_argmax2(dwmh_ctx* ctx, const float* softmax_dev, uint8_t* seg_dev, int64_t nvox, void* stream);
 
+/* --- `remove_sparks` (deepwmh/analysis/image_ops.py:325-344; called from predict.py:19-26,158-163) on the
+ * device: 6-connected components of seg_dev > 0 (scipy.ndimage.label's default), components with fewer than
+ * min_volume voxels are discarded, the rest become 1.  seg_dev / out_dev: uint8 [X][Y][Z], may alias.  The
+ * voxel-size rule of remove_3mm_sparks (:346-367) stays on the host (deepwmh_b200/preprocess.py). */
+int dwmh_remove_sparks(dwmh_ctx* ctx, const uint8_t* seg_dev, int32_t X, int32_t Y, int32_t Z, int32_t min_volume,
+                       uint8_t* out_dev, void* stream);
+
 /* --- a6 end to end with HOST buffers (what predict_preprocessed_data_return_seg_and_softmax does):
  * raw fp32 volume [X][Y][Z] in host memory -> (optional z-score, mask_mode as above, <0 = skip)
  * -> tiled prediction -> host softmax fp32 [2][X][Y][Z] and seg uint8 [X][Y][Z].  H2D/D2H inside. */

@@ -151,3 +151,35 @@ def test_cli_end_to_end_matches_oracle_pipeline(tmp_path):
     seg_ref, _ = O.OracleTrainer(plans, net).predict_preprocessed_data_return_seg_and_softmax(norm)
     full_ref = preprocess.paste_back(seg_ref.astype(np.uint8), vol_zyx.shape, bbox)
     assert np.mean(full_ref == seg) > 0.998
+
+
+@pytest.mark.gpu
+def test_device_remove_sparks_matches_scipy_components():
+    """dwmh_remove_sparks (union-find CCL on the device) is bit-identical to the scipy.ndimage.label loop of
+    image_ops.py:325-344, and remove_3mm_sparks applies the same voxel-size rule."""
+    import deepwmh_b200
+    plans = small_plans()
+    tr = deepwmh_b200.nnUNetTrainerV2(plans, device=0, max_batch=1)
+    net = tr.network
+    rng = np.random.default_rng(5)
+    for shape, thr in (((24, 24, 24), 0.82), ((37, 19, 45), 0.7), ((64, 80, 48), 0.55), ((5, 7, 3), 0.5), ((1, 1, 9), 0.4)):
+        m = (rng.random(shape) > thr).astype(np.uint8)
+        m_dev = torch.from_numpy(m).cuda()
+        for mv in (1, 2, 3, 24):
+            got = net.remove_sparks(m_dev, mv).cpu().numpy()
+            assert np.array_equal(got, preprocess.remove_sparks(m, mv).astype(np.uint8)), (shape, mv)
+        for vs in ([1.0, 1.0, 1.0], [0.5, 0.5, 0.5], [2.0, 2.0, 2.0], [1.0, 1.0, 6.0]):
+            got = net.remove_3mm_sparks(m_dev, vs).cpu().numpy()
+            assert np.array_equal(got, preprocess.remove_3mm_sparks(m, vs).astype(np.uint8)), (shape, vs)
+    z = torch.zeros((8, 8, 8), dtype=torch.uint8, device="cuda")
+    assert net.remove_sparks(z, 3).sum().item() == 0
+    o = torch.ones((8, 9, 10), dtype=torch.uint8, device="cuda")
+    assert net.remove_sparks(o, 3).sum().item() == 720
+    # a serpentine one-voxel-wide component exercises long union chains; labels > 1 in the input count as foreground
+    s = np.zeros((16, 16, 16), np.uint8)
+    for i in range(16):
+        s[i, :, 0 if i % 2 == 0 else 15] = 2
+        s[i, 15 if i % 2 == 0 else 0, :] = 2
+    got = net.remove_sparks(torch.from_numpy(s).cuda(), 3).cpu().numpy()
+    assert np.array_equal(got, preprocess.remove_sparks(s, 3).astype(np.uint8))
+    net.close()
