@@ -902,6 +902,25 @@ static int grow(V** p, size_t* cap, size_t need) {
   return 0;
 }
 
+// checkpoint ensemble of masked background probabilities (DCNN_multistage.py:102-125)
+extern "C" int dwmh_ensemble_masked_add(dwmh_ctx* c, float* acc, const float* bg_softmax, const float* valid_mask, int64_t n, void* stream_) {
+  if (!c || !acc || !bg_softmax) return fail("dwmh_ensemble_masked_add: null argument");
+  CU_TRY(cudaSetDevice(c->device));
+  ensemble_masked_add_kernel<<<c->num_sms * 8, 256, 0, (cudaStream_t)stream_>>>(acc, bg_softmax, valid_mask, n);
+  c->launches++;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+extern "C" int dwmh_ensemble_refine(dwmh_ctx* c, float* acc, int32_t k, uint8_t* label, int64_t n, void* stream_) {
+  if (!c || !acc) return fail("dwmh_ensemble_refine: null argument");
+  if (k <= 0) return fail("dwmh_ensemble_refine: k must be positive");
+  CU_TRY(cudaSetDevice(c->device));
+  ensemble_refine_kernel<<<c->num_sms * 8, 256, 0, (cudaStream_t)stream_>>>(acc, (float)k, label, n);
+  c->launches++;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 // remove_sparks (deepwmh/analysis/image_ops.py:325-344) on the device; seg and out may alias.
 extern "C" int dwmh_remove_sparks(dwmh_ctx* c, const uint8_t* seg, int32_t X, int32_t Y, int32_t Z, int32_t min_volume,
                                   uint8_t* out, void* stream_) {

@@ -68,3 +68,36 @@ def ensemble_mean(softmaxes: Sequence[torch.Tensor]) -> torch.Tensor:
     for s in softmaxes:
         acc += s
     return acc / float(len(softmaxes))
+
+
+def checkpoint_ensemble_refined_label(trainer, checkpoints: Sequence[dict], data, valid_mask=None, voxel_size=(1.0, 1.0, 1.0),
+                                      do_mirroring: bool = False):
+    """stage-2 label refinement of deepwmh/pipeline/DCNN_multistage.py:317-394 without the NIfTI round trips.
+    For each of the k epoch checkpoints: load it (`load_checkpoint_ram`), predict the volume (the reference disables TTA
+    here, :334-336), keep the BACKGROUND probability x; accumulate y = 1 - m (1 - x) (`_parallel_softmax_masking`), average
+    over k, label = field < 0.5, remove components below 3 mm^3 (`_parallel_ensembling`).
+    data: preprocessed [1, X, Y, Z]; valid_mask: [X, Y, Z] array / tensor or None.
+    -> (field fp32 [X, Y, Z], label uint8 [X, Y, Z]) as device tensors."""
+    net = trainer.network
+    k = len(checkpoints)
+    if k == 0:
+        raise ValueError("checkpoint_ensemble_refined_label: no checkpoints")
+    acc = None
+    m = None
+    if valid_mask is not None:
+        m = torch.as_tensor(np.ascontiguousarray(valid_mask) if isinstance(valid_mask, np.ndarray) else valid_mask)
+        m = m.to(device=net.device, dtype=torch.float32).contiguous()
+    for ck in checkpoints:
+        trainer.load_checkpoint_ram(ck, False)
+        _, softmax = trainer.predict_preprocessed_data_return_seg_and_softmax(
+            data, do_mirroring=do_mirroring, mirror_axes=trainer.data_aug_params["mirror_axes"], use_sliding_window=True,
+            step_size=0.5, use_gaussian=True, all_in_gpu=False, mixed_precision=True)
+        bg = torch.as_tensor(softmax[0]).to(device=net.device, dtype=torch.float32).contiguous()
+        if acc is None:
+            acc = torch.zeros_like(bg)
+        with torch.cuda.device(net.device):
+            net.ensemble_masked_add_(acc, bg, m)
+    with torch.cuda.device(net.device):
+        label = net.ensemble_refine_(acc, k)
+        label = net.remove_3mm_sparks(label, voxel_size)
+    return acc, label

@@ -160,6 +160,21 @@ class SegmentationNetwork:
         check(self._lib.dwmh_finalize(self._ctx, _ptr(agg), _ptr(wgt), _ptr(agg), _ptr(seg), X, Y, Z, _stream()))
         return seg, agg
 
+    def ensemble_masked_add_(self, acc: torch.Tensor, bg_softmax: torch.Tensor, valid_mask: Optional[torch.Tensor] = None):
+        """acc += 1 - m (1 - x): one checkpoint of `_parallel_softmax_masking` + `_parallel_ensembling`
+        (deepwmh/pipeline/DCNN_multistage.py:102-117), in place on fp32 device tensors."""
+        assert acc.is_cuda and acc.dtype == torch.float32 and acc.is_contiguous() and bg_softmax.shape == acc.shape
+        assert bg_softmax.dtype == torch.float32 and bg_softmax.is_contiguous()
+        if valid_mask is not None:
+            assert valid_mask.dtype == torch.float32 and valid_mask.is_contiguous() and valid_mask.shape == acc.shape
+        check(self._lib.dwmh_ensemble_masked_add(self._ctx, _ptr(acc), _ptr(bg_softmax), _ptr(valid_mask), acc.numel(), _stream()))
+
+    def ensemble_refine_(self, acc: torch.Tensor, k: int) -> torch.Tensor:
+        """acc /= k in place (the ensembled field) -> uint8 label `field < 0.5` (DCNN_multistage.py:118-119)."""
+        label = torch.empty(acc.shape, dtype=torch.uint8, device=acc.device)
+        check(self._lib.dwmh_ensemble_refine(self._ctx, _ptr(acc), int(k), _ptr(label), acc.numel(), _stream()))
+        return label
+
     def remove_sparks(self, seg: torch.Tensor, min_volume: int = 3) -> torch.Tensor:
         """`remove_sparks` (deepwmh/analysis/image_ops.py:325-344) on the device: uint8 label map [X,Y,Z] -> uint8 mask of the
         6-connected components with at least min_volume voxels."""

@@ -99,6 +99,14 @@ int dwmh_finalize(dwmh_ctx* ctx, const float* agg_dev, const float* wgt_dev, flo
 int dwmh_axpy(dwmh_ctx* ctx, float* acc_dev, const float* x_dev, float alpha, int64_t n, void* stream);
 int dwmh_argmax2(dwmh_ctx* ctx, const float* softmax_dev, uint8_t* seg_dev, int64_t nvox, void* stream);
 
+/* --- checkpoint ensemble with softmax masking (deepwmh/pipeline/DCNN_multistage.py:102-125,317-394).
+ * dwmh_ensemble_masked_add: acc += 1 - m (1 - x) for one checkpoint's BACKGROUND probability x (the fork's
+ * `<case>_0.nii.gz`), valid mask m (NULL = all ones), with the reference's rounding (float64 arithmetic, float32 storage).
+ * dwmh_ensemble_refine: acc /= k (the ensembled field, in place) and label = acc < 0.5 (label_dev may be NULL). */
+int dwmh_ensemble_masked_add(dwmh_ctx* ctx, float* acc_dev, const float* bg_softmax_dev, const float* valid_mask_dev,
+                             int64_t n, void* stream);
+int dwmh_ensemble_refine(dwmh_ctx* ctx, float* acc_dev, int32_t k, uint8_t* label_dev, int64_t n, void* stream);
+
 /* --- `remove_sparks` (deepwmh/analysis/image_ops.py:325-344; called from predict.py:19-26,158-163) on the
  * device: 6-connected components of seg_dev > 0 (scipy.ndimage.label's default), components with fewer than
  * min_volume voxels are discarded, the rest become 1.  seg_dev / out_dev: uint8 [X][Y][Z], may alias.  The

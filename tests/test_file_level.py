@@ -183,3 +183,67 @@ def test_device_remove_sparks_matches_scipy_components():
     got = net.remove_sparks(torch.from_numpy(s).cuda(), 3).cpu().numpy()
     assert np.array_equal(got, preprocess.remove_sparks(s, 3).astype(np.uint8))
     net.close()
+
+
+def _ref_masked_ensemble(xs, m, voxel_size):
+    """numpy restatement of _parallel_softmax_masking + _parallel_ensembling (DCNN_multistage.py:102-125): float64 file
+    values (nibabel get_fdata) of float32 NIfTIs, float32 running field."""
+    field = np.zeros(xs[0].shape).astype("float32")
+    for x in xs:
+        y = 1 - (m.astype(np.float64) * (1 - x.astype(np.float64)))
+        y = y.astype(np.float32).astype(np.float64)               # saved as float32, loaded as float64
+        field += y
+    field = field / len(xs)
+    label = (field < 0.5).astype("float32")
+    return field, preprocess.remove_3mm_sparks(label, voxel_size).astype(np.uint8)
+
+
+@pytest.mark.gpu
+def test_device_masked_ensemble_is_bit_exact():
+    """dwmh_ensemble_masked_add / dwmh_ensemble_refine reproduce the reference's masked checkpoint ensemble
+    bit for bit on the same background-probability inputs."""
+    import deepwmh_b200
+    plans = small_plans()
+    tr = deepwmh_b200.nnUNetTrainerV2(plans, device=0, max_batch=1)
+    net = tr.network
+    rng = np.random.default_rng(9)
+    shape = (33, 40, 29)
+    xs = [np.clip(rng.normal(0.5, 0.35, size=shape), 0, 1).astype(np.float32) for _ in range(5)]
+    xs[2][:4] = 0.5                                              # exact ties stay background (field < 0.5 is strict)
+    m = (rng.random(shape) > 0.3).astype(np.float32)
+    for mask in (m, None):
+        acc = torch.zeros(shape, dtype=torch.float32, device="cuda")
+        md = torch.from_numpy(mask).cuda() if mask is not None else None
+        for x in xs:
+            net.ensemble_masked_add_(acc, torch.from_numpy(x).cuda(), md)
+        label = net.ensemble_refine_(acc, len(xs))
+        clean = net.remove_3mm_sparks(label, [1.0, 1.0, 1.0])
+        f_ref, l_ref = _ref_masked_ensemble(xs, mask if mask is not None else np.ones(shape, np.float32), [1.0, 1.0, 1.0])
+        assert np.array_equal(acc.cpu().numpy(), f_ref)
+        assert np.array_equal(clean.cpu().numpy(), l_ref)
+    net.close()
+
+
+@pytest.mark.gpu
+def test_checkpoint_ensemble_refined_label_end_to_end():
+    """The k-checkpoint loop (load_checkpoint_ram -> no-TTA prediction -> masked mean -> < 0.5 -> 3 mm sparks) against the
+    same pipeline run with the oracle's predictions."""
+    import deepwmh_b200
+    from deepwmh_b200 import parallel
+    plans = small_plans()
+    nets = [O.build_benchmark_network(k, plans) for k in range(3)]
+    tr = deepwmh_b200.nnUNetTrainerV2(plans, device=0, max_batch=8)
+    vol = O.synthetic_flair((40, 44, 36), seed=3)
+    data = O.zscore_nnunet(vol[0], (vol[0] != 0).astype(np.int8) - 1, True)[None]
+    m = (vol[0] != 0).astype(np.float32)
+    field, label = parallel.checkpoint_ensemble_refined_label(tr, [{"state_dict": n.state_dict()} for n in nets], data, m, (1.0, 1.0, 1.0))
+    xs = []
+    for n in nets:
+        _, sm = O.OracleTrainer(plans, n).predict_preprocessed_data_return_seg_and_softmax(data, do_mirroring=False)
+        xs.append(sm[0].astype(np.float32))
+    f_ref, l_ref = _ref_masked_ensemble(xs, m, [1.0, 1.0, 1.0])
+    assert field.shape == f_ref.shape and label.dtype == torch.uint8
+    assert np.abs(field.cpu().numpy() - f_ref).max() < 1e-2
+    assert np.mean(label.cpu().numpy() == l_ref) > 0.995
+    assert (field.cpu().numpy()[m == 0] == 1.0).all()           # outside the valid mask the field is exactly "background"
+    tr.network.close()
