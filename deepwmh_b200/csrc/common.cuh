@@ -70,6 +70,17 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   return r;
 }
 
+// 256-bit global accesses (sm_100): two 16-byte voxel-chunks per instruction keep twice the bytes in flight per thread;
+// the pass is a pure stream and was bound by memory-level parallelism (2048 threads x 16 B per SM).
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 // Per-forward sample descriptor: where the patch sits in the padded volume and which axes are mirrored.
 struct SampleMeta {
   int32_t ox, oy, oz;     // tile origin in the volume (axis 0,1,2)

@@ -728,6 +728,28 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       for (int t = z_lo; t < z_end; ++t) {
         DWMH_TIMED_WAIT(w0_, tc::mbar_wait(acc_full + 8 * slot, phase, 7));
         tc::tc_fence_after();
+        if (p.osw == 2) {
+          // W-doubling (the usual case): the two W parities of a voxel are adjacent in memory, so a lane stores 32
+          // contiguous bytes (full sectors, 256-bit stores) per 8-channel chunk instead of two half-sector writes.
+          const int cpp = p.CBt >> 4;                              // 16-column chunks per parity block
+          int chq = 0;                                             // first chunk of parity (qa, qb, qw = 0)
+          for (int qa = 0; qa < p.osd; ++qa)
+            for (int qb = 0; qb < p.osh; ++qb, chq += 2 * cpp)
+              for (int cc = 0; cc < cpp; ++cc) {
+                uint32_t r[2][16];
+                tc::tmem_ld16(tm_lane + slot * CB + (chq + cc) * 16, r[0]);
+                tc::tmem_ld16(tm_lane + slot * CB + (chq + cpp + cc) * 16, r[1]);
+                tc::tmem_ld_wait();
+                if (valid) {
+                  float a0[16], a1[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) { a0[i] = __uint_as_float(r[0][i]); a1[i] = __uint_as_float(r[1][i]); }
+                  uint4* o = out_n + (size_t)((cb * p.CBt + cc * 16) >> 3) * Vo + ((size_t)(t * p.osd + qa) * Ho + (h * p.osh + qb)) * Wo + (size_t)w * 2;
+                  st_global_256(o, pack8<T>(a0), pack8<T>(a1));
+                  st_global_256(o + Vo, pack8<T>(a0 + 8), pack8<T>(a1 + 8));
+                }
+              }
+        } else {
         // two 16-column chunks per TMEM wait; the (parity, channel offset) of a chunk advances incrementally (no divisions)
         int cofs = 0, qa = 0, qb = 0, qw = 0;
         for (int ch = 0; ch < nch; ch += 2) {
@@ -751,6 +773,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               if (++qw == p.osw) { qw = 0; if (++qb == p.osh) { qb = 0; ++qa; } }
             }
           }
+        }
         }
         tc::tc_fence_before();
         __syncwarp();

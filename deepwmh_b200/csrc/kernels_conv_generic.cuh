@@ -357,17 +357,6 @@ __global__ void __launch_bounds__(128) conv_generic_kernel(ConvParams p) {
 // s2d[n][class][C/8][D/sd][H/sh][W/sw][8] with class order tc_s2d_class().
 struct S2dParams { void* dst; int D, H, W, sd, sh, sw; };
 
-// 256-bit global accesses (sm_100): two 16-byte voxel-chunks per instruction keep twice the bytes in flight per thread;
-// the pass is a pure stream and was bound by memory-level parallelism (2048 threads x 16 B per SM).
-__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
-  asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
-}
-__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
-  asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) instnorm_lrelu_kernel(const void* __restrict__ raw, int raw32, void* __restrict__ y, NormParams np,
                                                              int C, int64_t V, S2dParams sp) {
