@@ -58,6 +58,7 @@ struct TcKParams {
   int C0, C1, Cout, CB, KC, nkc, nkc0;
   int nclass, Jlo, Jhi, jmax, tiles_per_kc, Din;
   int out32;                                 // raw output stored as fp32 instead of T
+  int s222;                                  // stride (2,2,2): the standard 8 parity classes (straight-line issue path)
   int tconv, CBt, osd, osh, osw, Cout_t;   // transposed-conv mode: CB = osd*osh*osw * CBt, scatter epilogue
   TcClassDesc cls[8];
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
@@ -575,6 +576,67 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         __syncwarp();
         continue;
       }
+      if (p.s222 && zo_lo == t && zo_hi == t + 1 && fresh_from == zo_hi && 2 * CB <= 256) {
+        // ---- steady state of a stride-(2,2,2) conv, straight line: the 8 parity classes and their 1/2/2/4 in-plane taps
+        // are compile-time here (the tap loop below costs ~250 cycles per tap in loop / branch overhead alone, more than
+        // the two MMAs it issues).  Sub-plane t feeds output t (all classes) and t+1 (the four odd-depth classes, which
+        // come first: N = 2 CB); exactly output t+1 is new.
+        const uint32_t col0 = tmem + lo_slot * CB, col1 = (lo_slot + 1 == R) ? tmem : col0 + CB;
+        const bool wrap = lo_slot + 1 == R;
+        const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int cd = c >> 2, ph = (c >> 1) & 1, pw = c & 1;
+          const int tile0 = cd * 9 + (ph ? (pw ? 5 : 3) : (pw ? 1 : 0));
+          for (int kc = 0; kc < p.nkc; ++kc) {
+            if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
+            tc::tc_fence_after();
+            { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
+            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            const uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + tile0) * tile16;
+#pragma unroll
+            for (int iy = 0; iy < (ph ? 2 : 1); ++iy) {
+#pragma unroll
+              for (int ix = 0; ix < (pw ? 2 : 1); ++ix) {
+                const int dy = ph ? iy : 1, dx = pw ? ix : 1, ti = iy * (pw ? 2 : 1) + ix;
+                uint32_t b_lo0;
+                if (p.resident) b_lo0 = b_res + ti * tile16;
+                else {
+                  if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
+                  tc::tc_fence_after();
+                  b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+                  { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
+                }
+                if (leader) {
+#pragma unroll
+                  for (int kk = 0; kk < KSTEPS; ++kk) {
+                    const uint64_t adesc = tc_desc(a_hi, a_lo0 + dy * TC_PW + dx + kk * (2 * TC_PLANE_BYTES >> 4));
+                    const uint32_t bl = b_lo0 + kk * kstep_b;
+                    if (cd == 0) {
+                      const bool first_site = c == 0 && kk == 0;             // the step's first MMA overwrites output t+1
+                      if (wrap || (first_site && kc == 0)) {
+                        tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), idesc1, 1u);
+                        tc::umma_f16(col1, adesc, tc_desc(b_hi, bl + CB), idesc1, (first_site && kc == 0) ? 0u : 1u);
+                      } else tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), id2, 1u);
+                    } else tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), idesc1, 1u);
+                  }
+                }
+                if (!p.resident) {
+                  if (elected) tc::umma_commit(b_empty + 8 * b.idx);
+                  b.advance(NB);
+                }
+              }
+            }
+            if (elected) tc::umma_commit(a_empty + 8 * a.idx);
+            a.advance(SA);
+          }
+        }
+        if (elected) tc::umma_commit(acc_full + 8 * done.idx);        // output plane t is complete
+        done.advance(R);
+        ++next_done;
+        __syncwarp();
+        continue;
+      }
       if (p.Jlo == 0 && zo_lo == t && zo_hi == t + 1 && fresh_from == zo_hi && 2 * CB <= 256) {
         // ---- steady state of a depth-strided conv: sub-plane t feeds output t (all classes) and t+1 (odd-depth
         // classes, N = 2 CB); exactly output t+1 is new.  No segment bookkeeping, two MMAs only at the ring wrap.
@@ -1011,6 +1073,16 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
         tile0 += (int)cls_taps[c].size();
       }
   kp.tiles_per_kc = tile0;
+  // the straight-line stride-(2,2,2) issue path hard-codes this table: verify it instead of assuming it
+  kp.s222 = (sd == 2 && sh == 2 && sw == 2 && kp.nclass == 8 && tile0 == 18) ? 1 : 0;
+  for (int c = 0; c < 8 && kp.s222; ++c) {
+    const int cd = c >> 2, ph = (c >> 1) & 1, pw = c & 1;
+    int mask = 0;
+    for (int iy = 0; iy < (ph ? 2 : 1); ++iy)
+      for (int ix = 0; ix < (pw ? 2 : 1); ++ix) mask |= 1 << ((ph ? iy : 1) * 3 + (pw ? ix : 1));
+    const TcClassDesc& d = kp.cls[c];
+    if (d.tapmask != mask || d.tile0 != cd * 9 + (ph ? (pw ? 5 : 3) : (pw ? 1 : 0)) || d.jlo != 0 || d.jcnt != (cd == 0 ? 2 : 1)) kp.s222 = 0;
+  }
   // ---- tiling / shared-memory plan ----
   int KC0 = 64;
   while (KC0 > 16 && (c0 % KC0 || c1 % KC0)) KC0 >>= 1;
