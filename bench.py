@@ -274,7 +274,7 @@ def run_b200(args):
     achieved = tc_tflop / (tc_ms / 1e3)            # dominant kernel: conv3_tc_kernel (all tcgen05 conv / tconv launches)
     # bounded CPU sample: 3 tile-forwards of the same workload on all host cores
     cores = os.cpu_count()
-    cpu_t = cpu_forward_sample(1 + args.cpu_forwards, cores)[1:] if args.cpu_forwards > 0 else []
+    cpu_t = cpu_forward_sample(1 + args.cpu_forwards, cores)[1:] if (args.cpu_forwards > 0 and world == 1) else []      # N = 1 only
     cpu = None
     if cpu_t:
         per = sum(cpu_t) / len(cpu_t)
