@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle as O  # noqa: E402
 import deepwmh_b200  # noqa: E402
 from deepwmh_b200.parallel import predict_volume_tile_sharded, shard_cohort  # noqa: E402

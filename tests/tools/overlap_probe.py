@@ -2,7 +2,7 @@
 host threads / streams and compares with running them back to back."""
 import os, sys, threading, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle as O
 import deepwmh_b200
 

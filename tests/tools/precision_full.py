@@ -13,7 +13,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle as O  # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
@@ -142,7 +142,7 @@ def main():
     t0 = time.time()
     seg_r, p_r = predict(net, data)
     print("fp32 oracle on GPU: %.1fs, fg=%.4f" % (time.time() - t0, seg_r.mean()))
-    gpath = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "v1_tta.npz")
+    gpath = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "v1_tta.npz")
     if os.path.exists(gpath):
         g = np.load(gpath)
         seg_g = np.unpackbits(g["seg_bits"])[: seg_r.size].reshape(seg_r.shape)

@@ -25,7 +25,7 @@ for row in csv.DictReader(lines):
 sel = [per[i] for i in order[-n_last:]]
 tc = [x for x in sel if x["kernel"].startswith("conv3_tc_kernel")]
 tot = sum(x.get("dram__bytes_read.sum", 0) + x.get("dram__bytes_write.sum", 0) for x in tc)
-res = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none, tools/profile_forward.py 32 1 (one batch of 32 tile-forwards)",
+res = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none, tests/tools/profile_forward.py 32 1 (one batch of 32 tile-forwards)",
        "tc_launches": len(tc), "tc_dram_bytes_total": tot, "tc_dram_bytes_per_launch": tot / max(len(tc), 1),
        "all_dram_bytes_total": sum(x.get("dram__bytes_read.sum", 0) + x.get("dram__bytes_write.sum", 0) for x in sel),
        "launches": [{"kernel": x["kernel"][:60], "grid": x["grid"], "ms": round(x.get("gpu__time_duration.sum", 0), 4),
