@@ -59,6 +59,8 @@ struct TcKParams {
   int nclass, Jlo, Jhi, jmax, tiles_per_kc, Din;
   int out32;                                 // raw output stored as fp32 instead of T
   int s222;                                  // stride (2,2,2): the standard 8 parity classes (straight-line issue path)
+  int mcast;                                 // debug: 0 = cluster launch but every CTA loads its own weight tiles
+  int cluster;                               // 2: CTA pairs (thread-block cluster) share every streamed weight tile by TMA multicast
   int tconv, CBt, osd, osh, osw, Cout_t;   // transposed-conv mode: CB = osd*osh*osw * CBt, scatter epilogue
   TcClassDesc cls[8];
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
@@ -135,6 +137,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   float* s_coef = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)g * 2 * 64;   // XFORM: a[64], b[64]
   float* s_slice = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)p.G * 2 * 64 + (size_t)g * 4 * TC_FIRST_SLICE;   // FIRST: 4-slot ring of haloed input slices
   const uint32_t smem_a = smem_base + (uint32_t)g * SA * p.a_stage_bytes;          // this group's activation ring
+  // UMMA shared-memory descriptors hold a 14-bit (address >> 4): CTA-relative.  In a cluster launch the shared::cta window of
+  // rank > 0 sits above 256 KB in the 32-bit shared address space, so descriptor arithmetic uses the masked offsets.
+  const uint32_t smem_a_d = smem_a & 0x3FFFFu, smem_b_d = (smem_base + p.off_b) & 0x3FFFFu;
   const uint32_t s_full = smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + (uint32_t)g * 64u, s_empty = s_full + 32u;   // FIRST: slice ring barriers
 
   if (threadIdx.x == 0) {
@@ -154,6 +159,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tc::mbar_init(smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + gg * 64 + 8 * s_, 1);
           tc::mbar_init(smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + gg * 64 + 32 + 8 * s_, 2);
         }
+    if (p.cluster > 1)
+      for (uint32_t s_ = 0; s_ < NB; ++s_) tc::mbar_init(smem_base + p.off_bar + TC_SMEM_RESERVED - 512 + 8 * s_, p.cluster - 1);
     const uint32_t nactive = (uint32_t)min(p.G, p.total_items - (int)blockIdx.x * p.G);      // groups of this CTA that have a tile
     for (uint32_t s_ = 0; s_ < NB; ++s_) { tc::mbar_init(b_full + 8 * s_, 1); tc::mbar_init(b_empty + 8 * s_, nactive); }
     tc::fence_barrier_init();
@@ -172,6 +179,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  if (p.cluster > 1) tc::cluster_sync();          // the peer's barriers exist before anyone arrives on them remotely
   const uint32_t tmem = *tmem_ptr_smem + (uint32_t)g * 256u;       // group 1 owns TMEM columns 256..511
   const bool prof_on = (p.dbg & 8) != 0;
   long long w0_ = 0, w1_ = 0, w2_ = 0, w3_ = 0;      // profiling (dbg & 8): barrier waits, issue bursts, general-path time
@@ -401,6 +409,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
         }
     } else if (g == 0) {     // streamed weight tiles are shared by the groups of the CTA (same cout block, same plane range)
+      const uint32_t crank = p.cluster > 1 ? tc::cluster_ctarank() : 0;
       RingPos b;
       for (int t = z_lo - p.Jhi; t <= z_end - 1 - p.Jlo; ++t) {
         if (t < 0 || t >= p.Din) continue;
@@ -411,7 +420,18 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             for (int ti = 0; ti < ntaps; ++ti) {
               const int tile = kc * p.tiles_per_kc + p.cls[c].tile0 + ti;
               DWMH_TIMED_WAIT(w0_, tc::mbar_wait(b_empty + 8 * b.idx, b.phase ^ 1, 2));
-              if (leader) {
+              if (p.cluster > 1 && p.mcast) {
+                // CTA pair: every CTA arms its own b_full, rank 1 then tells rank 0 that its slot is free, rank 0 issues ONE
+                // multicast copy that lands in both CTAs (half the L2 weight traffic of the streamed layers)
+                const uint32_t peer_empty = smem_base + p.off_bar + TC_SMEM_RESERVED - 512 + 8 * b.idx;
+                if (leader) tc::mbar_arrive_expect_tx(b_full + 8 * b.idx, p.b_tile_bytes);
+                __syncwarp();
+                if (crank != 0) { if (leader) tc::mbar_arrive_remote(peer_empty, 0); }
+                else {
+                  DWMH_TIMED_WAIT(w0_, tc::mbar_wait_cluster(peer_empty, b.phase, 12));
+                  if (leader) tc::bulk_load_multicast(smem_base + p.off_b + b.idx * p.b_tile_bytes, wsrc + (size_t)tile * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * b.idx, (uint16_t)((1u << p.cluster) - 1));
+                }
+              } else if (leader) {
                 tc::mbar_arrive_expect_tx(b_full + 8 * b.idx, p.b_tile_bytes);
                 tc::bulk_load(smem_base + p.off_b + b.idx * p.b_tile_bytes, wsrc + (size_t)tile * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * b.idx);
               }
@@ -432,7 +452,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t idesc = tc::instr_desc_f16(p.fmt, 128, (int)CB);
       const uint32_t hi_desc = (128u >> 4) | (1u << 14);                  // SBO = 128 B for both operands
       const uint32_t a_lbo = (2048u >> 4) << 16, b_lbo = ((CB * 16u) >> 4) << 16;
-      const uint32_t b_lo0 = ((smem_base + p.off_b) >> 4) | b_lbo;
+      const uint32_t b_lo0 = (smem_b_d >> 4) | b_lbo;
       tc::mbar_wait(b_full, 0, 5);
       RingPos a, fresh, done;
       for (int t = z_lo; t < z_end; ++t) {
@@ -440,7 +460,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4);
         tc::tc_fence_after();
         if (leader) {
-          const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo;
+          const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo;
           const uint32_t col = tmem + fresh.idx * CB;
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
@@ -460,7 +480,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const uint32_t a_hi = (uint32_t)((TC_PW * 16) >> 4) | (1u << 14);  // SBO = 160 B, descriptor version 1
     const uint32_t b_hi = (128u >> 4) | (1u << 14);                    // SBO = 128 B
     const uint32_t a_lbo_field = (uint32_t)(TC_PLANE_BYTES >> 4) << 16;
-    const uint32_t b_lo_res = ((smem_base + p.off_b) >> 4) | (b_lbo16 << 16);
+    const uint32_t b_lo_res = (smem_b_d >> 4) | (b_lbo16 << 16);
     const int t_first = z_lo - p.Jhi, t_last_nominal = z_end - 1 - p.Jlo;
     const int last_t = min(t_last_nominal, p.Din - 1);
     const bool plain = p.nclass == 1 && p.Jlo == -1 && p.Jhi == 1;     // stride-1 3x3x3
@@ -497,12 +517,12 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const long long tb_ = prof_on ? clock64() : 0;
           if (!p.resident) {
             // streamed weight tiles: one ring slot per tap, shared by the groups of the CTA
-            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
 #pragma unroll
             for (int sft = 0; sft < 9; ++sft) {
               if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
               tc::tc_fence_after();
-              const uint32_t b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+              const uint32_t b_lo0 = ((smem_b_d + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
               { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
               if (leader) {
 #pragma unroll
@@ -529,7 +549,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               b.advance(NB);
             }
           } else if (leader && !wrap) {
-            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
 #pragma unroll
             for (int sft = 0; sft < 9; ++sft) {
@@ -546,7 +566,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               bl += tile16;
             }
           } else if (leader) {
-            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
 #pragma unroll
             for (int sft = 0; sft < 9; ++sft) {
@@ -592,7 +612,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
             tc::tc_fence_after();
             { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
-            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             const uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + tile0) * tile16;
 #pragma unroll
             for (int iy = 0; iy < (ph ? 2 : 1); ++iy) {
@@ -604,7 +624,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 else {
                   if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
                   tc::tc_fence_after();
-                  b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+                  b_lo0 = ((smem_b_d + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
                   { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
                 }
                 if (leader) {
@@ -650,7 +670,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
             tc::tc_fence_after();
             { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
-            const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+            const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0) * tile16;
             for (int m = tapmask; m; m &= m - 1) {
               const int sft = __ffs(m) - 1;
@@ -659,7 +679,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               else {
                 if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
                 tc::tc_fence_after();
-                b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+                b_lo0 = ((smem_b_d + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
                 { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
               }
               const uint32_t a_lo1 = a_lo0 + (uint32_t)((kTapShift >> (5 * sft)) & 31u);
@@ -720,7 +740,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           a_peek = false;
           tc::tc_fence_after();
-          const uint32_t a_lo0 = ((smem_a + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+          const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
           uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0) * tile16;
           for (int m = tapmask; m; m &= m - 1) {
             const int sft = __ffs(m) - 1;
@@ -729,7 +749,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             else {
               if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
               tc::tc_fence_after();
-              b_lo0 = ((smem_base + p.off_b + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+              b_lo0 = ((smem_b_d + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
               { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }   // consumed at the next tap
             }
             const uint32_t a_lo1 = a_lo0 + (uint32_t)((kTapShift >> (5 * sft)) & 31u);
@@ -953,6 +973,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         atomicAdd(p.sums + ((size_t)n * p.Cout + (size_t)cb * CB + c) * 2 + which, (double)s_stat[i]);
       }
   }
+  if (p.cluster > 1) tc::cluster_sync();          // no CTA of a pair leaves while its peer may still signal it
   if (warp_abs == 1) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -1324,6 +1345,21 @@ inline int tc_set_attr_all() {
 
 inline int tc_init_attributes(bool bf16) { return bf16 ? tc_set_attr_all<__nv_bfloat16>() : tc_set_attr_all<__half>(); }
 
+// plain launch, or a launch in thread-block clusters of `cluster` CTAs along x (weight multicast)
+template <typename Kern>
+inline void tc_do_launch(Kern kern, unsigned grid, unsigned threads, size_t smem, cudaStream_t st, int cluster,
+                         const CUtensorMap& tm0, const CUtensorMap& tm1, const TcKParams& kp) {
+  if (cluster > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(threads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, tm0, tm1, kp);
+  } else kern<<<grid, threads, smem, st>>>(tm0, tm1, kp);
+}
+
 struct TcXform { const double* sums; const float* gamma; const float* beta; float inv_count; const void* src; };
 struct TcFirstSrc { const float* src; const SampleMeta* metas; int patch_mode, SY, SZ; };
 
@@ -1346,6 +1382,15 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   // one (n, cb) when the tiles x z-blocks count is even
   if (!kp.first && kp.G == 2 && (kp.resident ? ((long long)kp.nzb * tiles) % 2 != 0 : tiles % 2 != 0)) kp.G = 1;    // (streamed weights: same z-block too)
   kp.total_items = (int)items;
+  // CTA pairs (clusters of 2) for streamed weights: both CTAs must walk the same tile sequence -> same (n, cout block, z-block)
+  {
+    static int allow_cluster = -1;
+    if (allow_cluster < 0) { const char* e = getenv("DWMH_TC_CLUSTER"); allow_cluster = e ? atoi(e) : 1; }
+    kp.mcast = allow_cluster == 1;
+    kp.cluster = (allow_cluster && !kp.resident && !kp.tconv && !kp.first && !kp.xform && tiles % (2 * kp.G) == 0) ? 2 : 1;
+  }
+  const int launch_cluster = kp.cluster;
+  { const char* e = getenv("DWMH_TC_CLUSTER"); if (e && atoi(e) == 3) kp.cluster = 1; }      // debug: cluster launch, cluster code off
   const unsigned grid = (unsigned)((items + kp.G - 1) / kp.G);
   const unsigned threads = TC_THREADS * kp.G;
   static unsigned long long* prof_dev = nullptr;
@@ -1356,7 +1401,7 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   kp.prof = prof_dev;
   const int ks = kp.KC / 16;
   const bool small = kp.CB <= 32 && !kp.tconv;
-#define DWMH_TC_LAUNCH(K, S, C, D) conv3_tc_kernel<T, K, S, C, D, false><<<grid, threads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
+#define DWMH_TC_LAUNCH(K, S, C, D) tc_do_launch(conv3_tc_kernel<T, K, S, C, D, false>, grid, threads, t.smem_bytes, st, launch_cluster, t.tm0, t.tm1, kp)
 #define DWMH_TC_LAUNCH_K(S, C, D) do { if (ks == 1) DWMH_TC_LAUNCH(1, S, C, D); else if (ks == 2) DWMH_TC_LAUNCH(2, S, C, D); else DWMH_TC_LAUNCH(4, S, C, D); } while (0)
   if (kp.first) conv3_tc_kernel<T, 2, true, false, true, false, true><<<grid, 512, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
   else if (kp.xform) {
