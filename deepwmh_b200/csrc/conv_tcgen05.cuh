@@ -1384,8 +1384,10 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   kp.total_items = (int)items;
   // CTA pairs (clusters of 2) for streamed weights: both CTAs must walk the same tile sequence -> same (n, cout block, z-block)
   {
-    static int allow_cluster = -1;
-    if (allow_cluster < 0) { const char* e = getenv("DWMH_TC_CLUSTER"); allow_cluster = e ? atoi(e) : 1; }
+    // opt-in (DWMH_TC_CLUSTER=1; read per launch so that a test can toggle it): measured neutral on the benchmark -- the
+    // streamed layers are not bound by L2 weight traffic ("What did not work")
+    const char* e = getenv("DWMH_TC_CLUSTER");
+    const int allow_cluster = e ? atoi(e) : 0;
     kp.mcast = allow_cluster == 1;
     kp.cluster = (allow_cluster && !kp.resident && !kp.tconv && !kp.first && !kp.xform && tiles % (2 * kp.G) == 0) ? 2 : 1;
   }

@@ -62,3 +62,34 @@ def test_tcgen05_layers_match_cuda_core_layers(cfg):
         p_or = torch.softmax(net(x.cpu()), 1)
     assert (p_tc.cpu() - p_or).abs().max().item() < 1e-2
     tr.network.close()
+
+
+@pytest.mark.gpu
+def test_cluster_multicast_of_streamed_weights_matches_plain_launch():
+    """DWMH_TC_CLUSTER=1: CTA pairs (thread-block clusters) receive every streamed weight tile by one TMA multicast.  Same
+    arithmetic, so the layer outputs must agree with the plain launch (up to the order of the statistics atomics)."""
+    import deepwmh_b200
+    plans = small_plans(patch=(32, 40, 24), pools=((2, 2, 2),) * 2, base=64)      # 128-channel layers: streamed, 4 tiles per plane
+    net = O.build_benchmark_network(0, plans)
+    tr = deepwmh_b200.nnUNetTrainerV2(plans, device=0, max_batch=3)
+    tr.load_checkpoint_ram({"state_dict": net.state_dict()}, False)
+    nw = tr.network
+    x = torch.randn(3, 1, 32, 40, 24, generator=torch.Generator().manual_seed(1)).cuda()
+    old = os.environ.get("DWMH_TC_CLUSTER")
+    try:
+        os.environ["DWMH_TC_CLUSTER"] = "0"
+        p0 = nw.forward_patches(x).clone()
+        ref = [nw.layer_output(i, 3).clone() for i in range(nw.num_layers())]
+        os.environ["DWMH_TC_CLUSTER"] = "1"
+        p1 = nw.forward_patches(x)
+        for i in range(nw.num_layers()):
+            got = nw.layer_output(i, 3)
+            assert torch.isfinite(got).all(), i
+            assert (got - ref[i]).abs().max().item() <= 2e-3 * ref[i].abs().max().item() + 1e-6, i
+        assert (p1 - p0).abs().max().item() < 2e-3
+    finally:
+        if old is None:
+            os.environ.pop("DWMH_TC_CLUSTER", None)
+        else:
+            os.environ["DWMH_TC_CLUSTER"] = old
+    nw.close()
