@@ -35,6 +35,7 @@ static int fail(const char* fmt, ...) {
 #define DW_TRY(expr) do { int r__ = (expr); if (r__) return r__; } while (0)
 
 extern "C" const char* dwmh_last_error(void) { return g_err.c_str(); }
+extern "C" void dwmh_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }   // for the other translation units (stage1.cu)
 extern "C" int dwmh_version(void) { return 100; }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,213 @@
+"""Stage-1 NLL anomaly map on the device.
+
+Host-side mirror of the array functions the reference uses in `nll_analysis`
+(deepwmh/analysis/lesion_analysis.py:115-181): same names, argument meaning and defaults as
+
+    z_score, mean_std_grid, median_filter, median_3mm, group_mean, group_std   deepwmh/analysis/image_ops.py
+    nll                                                                        deepwmh/analysis/lesion_analysis.py:84-113
+
+over the `dwmh_s1_*` entry points of include/deepwmh_b200.h.  Inputs may be numpy arrays or CUDA tensors [X, Y, Z];
+results are fp32 CUDA tensors.  There is no CPU path: every function needs the library and a GPU.
+
+Not built: the Otsu branches (`apply_otsu`, `nll(use_mask=True)` -- skimage), `component_filtering` (2-D per-slice
+erosion + largest component: host-side mask preparation), the histogram / threshold search and the NIfTI / plot output.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+Array = Union[np.ndarray, torch.Tensor]
+
+
+def _dev(t: Array, device: int, copy: bool = False) -> torch.Tensor:
+    """fp32 contiguous CUDA tensor (a fresh one when `copy`, so in-place kernels never touch the caller's data)."""
+    if isinstance(t, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(t, dtype=np.float32)).to(f"cuda:{device}")
+    out = t.to(device=f"cuda:{device}", dtype=torch.float32).contiguous()
+    if copy and out.data_ptr() == t.data_ptr():
+        out = out.clone()
+    return out
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device: int) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _i3(v: Sequence[int]):
+    if len(v) != 3:
+        raise ValueError("expected three values, got %r" % (v,))
+    return (C.c_int32 * 3)(*[int(a) for a in v])
+
+
+def _check3d(t: torch.Tensor, what: str):
+    if t.dim() != 3:
+        raise ValueError(f"{what} must be a 3-D volume, got shape {tuple(t.shape)}")
+
+
+def z_score(data: Array, mask: Optional[Array] = None, fill_outside: bool = False, device: int = 0,
+            return_stats: bool = False):
+    """image_ops.py:172-179.  `fill_outside=True` also replaces the voxels outside the mask by the minimum inside it
+    (lesion_analysis.py:150-151 / 160-161)."""
+    lib = _lib.load()
+    x = _dev(data, device, copy=True)
+    m = _dev(mask, device) if mask is not None else None
+    if m is not None and m.shape != x.shape:
+        raise ValueError("z_score: mask shape %s != data shape %s" % (tuple(m.shape), tuple(x.shape)))
+    ws = torch.empty(16, dtype=torch.float64, device=x.device)
+    stats = (C.c_double * 3)() if return_stats else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dwmh_s1_zscore(device, _ptr(x), _ptr(m), x.numel(), int(bool(fill_outside)), _ptr(ws), stats, _stream(device)))
+    return (x, tuple(stats)) if return_stats else x
+
+
+def mean_std_grid(data: Array, patch_size: Sequence[int], order: int = 1, mask: Optional[Array] = None,
+                  device: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """image_ops.py:56-170 (order 1, the value every call site in the reference uses)."""
+    if order != 1:
+        raise NotImplementedError("mean_std_grid: only order=1 (linear) is built; the reference never passes another order")
+    lib = _lib.load()
+    x = _dev(data, device)
+    _check3d(x, "mean_std_grid: data")
+    m = _dev(mask, device) if mask is not None else None
+    if m is not None and m.shape != x.shape:
+        raise ValueError("mean_std_grid: mask shape %s != data shape %s" % (tuple(m.shape), tuple(x.shape)))
+    X, Y, Z = (int(v) for v in x.shape)
+    ps = _i3(patch_size)
+    nbytes = C.c_int64(0)
+    _lib.check(lib.dwmh_s1_mean_std_grid_workspace(X, Y, Z, ps, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+    mean, std = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dwmh_s1_mean_std_grid(device, _ptr(x), _ptr(m), X, Y, Z, ps, _ptr(mean), _ptr(std), _ptr(ws), _stream(device)))
+    return mean, std
+
+
+def align_local_mean_(x: torch.Tensor, local_mu: torch.Tensor, target_local_mu: torch.Tensor) -> torch.Tensor:
+    """lesion_analysis.py:166-169: x_i = x_i - x_i_local_mu + x_prime_local_mu, in place."""
+    lib = _lib.load()
+    device = x.device.index
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dwmh_s1_align_local_mean(device, _ptr(x), _ptr(local_mu), _ptr(target_local_mu), x.numel(), _stream(device)))
+    return x
+
+
+def _side(side: Optional[str]) -> int:
+    assert side in [None, "+", "-"]
+    return {None: 0, "+": 1, "-": -1}[side]
+
+
+def nll(x_prime: Array, x_refs: Sequence[Array], min_std: Optional[float] = None, side: Optional[str] = None,
+        return_all: bool = False, use_mask: bool = False, mul_mask: Optional[Array] = None, device: int = 0):
+    """lesion_analysis.py:84-113.  `mul_mask` (not in the reference signature) fuses the `anomaly * m_valid_score`
+    that follows every call (:175, :184)."""
+    if use_mask:
+        raise NotImplementedError("nll(use_mask=True) needs skimage's Otsu threshold, which is not built")
+    lib = _lib.load()
+    x = _dev(x_prime, device)
+    refs = [_dev(r, device) for r in x_refs]
+    if not refs:
+        raise ValueError("nll: no reference images")
+    for r in refs:
+        if r.shape != x.shape:
+            raise ValueError("nll: reference shape %s != target shape %s" % (tuple(r.shape), tuple(x.shape)))
+    mm = _dev(mul_mask, device) if mul_mask is not None else None
+    an = torch.empty_like(x)
+    mu = torch.empty_like(x) if return_all else None
+    sg = torch.empty_like(x) if return_all else None
+    ptrs = (C.c_void_p * len(refs))(*[r.data_ptr() for r in refs])
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dwmh_s1_group_nll(device, _ptr(x), ptrs, len(refs), -1.0 if min_std is None else float(min_std), _side(side),
+                                         _ptr(mm), _ptr(an), _ptr(mu), _ptr(sg), x.numel(), _stream(device)))
+    return (an, mu, sg) if return_all else an
+
+
+def group_mean(data_list: Sequence[Array], masks=None, device: int = 0) -> torch.Tensor:
+    """image_ops.py:216-231 (masks=None)."""
+    return _group(data_list, masks, device)[0]
+
+
+def group_std(data_list: Sequence[Array], masks=None, device: int = 0) -> torch.Tensor:
+    """image_ops.py:199-214 (masks=None): population std."""
+    return _group(data_list, masks, device)[1]
+
+
+def _group(data_list, masks, device):
+    if masks is not None:
+        raise NotImplementedError("group_mean / group_std with masks (the Otsu branch of nll) is not built")
+    lib = _lib.load()
+    refs = [_dev(r, device) for r in data_list]
+    mu, sg = torch.empty_like(refs[0]), torch.empty_like(refs[0])
+    ptrs = (C.c_void_p * len(refs))(*[r.data_ptr() for r in refs])
+    with torch.cuda.device(refs[0].device):
+        # min_std = 0: sigma is returned unmodified
+        _lib.check(lib.dwmh_s1_group_nll(device, _ptr(refs[0]), ptrs, len(refs), 0.0, 0, None, None, _ptr(mu), _ptr(sg),
+                                         refs[0].numel(), _stream(device)))
+    return mu, sg
+
+
+def median_filter(data: Array, kernel_size: Sequence[int], device: int = 0) -> torch.Tensor:
+    """image_ops.py:181-183: scipy.ndimage.median_filter(size=kernel_size, mode='constant', cval=0), 3-D."""
+    lib = _lib.load()
+    x = _dev(data, device)
+    _check3d(x, "median_filter: data")
+    out = torch.empty_like(x)
+    X, Y, Z = (int(v) for v in x.shape)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dwmh_s1_median_filter(device, _ptr(x), _ptr(out), X, Y, Z, _i3(kernel_size), _stream(device)))
+    return out
+
+
+def median_kernel_size(physical_voxel_size: Sequence[float]) -> List[int]:
+    """The kernel rule of median_3mm (image_ops.py:378-421): int(3 mm / voxel) per axis, at least 3; thick-slice data
+    (max / min > 4) is filtered slice by slice, i.e. with size 1 along the thick axis."""
+    vs = [float(v) for v in physical_voxel_size]
+    ks = [max(3, int(3.0 / v)) for v in vs]
+    if max(vs) / min(vs) > 4.0:
+        ks[int(np.argmax(vs))] = 1
+    return ks
+
+
+def median_3mm(data: Array, physical_voxel_size: Sequence[float], device: int = 0) -> torch.Tensor:
+    return median_filter(data, median_kernel_size(physical_voxel_size), device=device)
+
+
+def image_patch_size(physical_voxel_size: Sequence[float], physical_patch_size=(50, 50, 50)) -> List[int]:
+    """lesion_analysis.py:124-131: the 50 mm local-mean patch in voxels."""
+    return [int(np.ceil(p / v)) for p, v in zip(physical_patch_size, physical_voxel_size)]
+
+
+def nll_anomaly_map(x_prime: Array, x_refs: Sequence[Array], m_rough_brain: Array, m_valid_score: Array,
+                    physical_voxel_size: Sequence[float] = (1.0, 1.0, 1.0), intensity_prior: Optional[str] = None,
+                    mean_correction: bool = True, min_std: float = 0.03, image_patch: Optional[Sequence[int]] = None,
+                    with_reference_scores: bool = False, device: int = 0) -> dict:
+    """The array part of `nll_analysis` (lesion_analysis.py:142-186) from raw registered volumes and the two masks:
+    z-score over the rough brain mask + tissue-min fill (target and every reference), 50 mm local-mean alignment of the
+    references to the target, voxelwise Gaussian NLL with sigma floored at `min_std`, masked by the valid-score mask.
+    -> dict of fp32 CUDA tensors: normalized_input, local_mean (masked as at :170), anomaly, mean, std
+       [+ reference_anomalies, :179-185]."""
+    assert intensity_prior in [None, "+", "-"], 'Unknown intensity prior "%s".' % str(intensity_prior)
+    patch = list(image_patch) if image_patch is not None else image_patch_size(physical_voxel_size)
+    brain = _dev(m_rough_brain, device)
+    valid = _dev(m_valid_score, device)
+    xp = z_score(x_prime, brain, fill_outside=True, device=device)
+    refs = [z_score(r, brain, fill_outside=True, device=device) for r in x_refs]
+    mu_p, _ = mean_std_grid(xp, patch, mask=valid, device=device)
+    if mean_correction:
+        for r in refs:
+            mu_i, _ = mean_std_grid(r, patch, mask=valid, device=device)
+            align_local_mean_(r, mu_i, mu_p)
+    an, mean, std = nll(xp, refs, min_std=min_std, side=intensity_prior, return_all=True, mul_mask=valid, device=device)
+    out = {"normalized_input": xp, "local_mean": mu_p * valid, "anomaly": an, "mean": mean, "std": std}
+    if with_reference_scores:
+        out["reference_anomalies"] = [nll(r, refs, min_std=min_std, side=intensity_prior, mul_mask=valid, device=device) for r in refs]
+    return out

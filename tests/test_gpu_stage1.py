@@ -1,0 +1,138 @@
+"""SURVEY.md section 8f-4 on the device: deepwmh_b200/stage1.py (dwmh_s1_* through the C ABI) against
+
+  * tests/golden/intree_v1.npz -- outputs of the REFERENCE'S OWN functions (tests/golden/make_golden_intree.py), and
+  * oracle/intree_oracle.py on seeded inputs, at small sizes and at BASELINE.json's 182x218x182.
+
+Tolerances: the device stores fp32 and computes each voxel in fp64; the reference computes in the dtype numpy promotes
+to (float32 sums for float32 inputs in group_mean / group_std, float64 after z_score).  Integer / selection work (median
+filter) is bit-exact.  The NLL magnifies input differences by (x - mu) / sigma^2 <= ~1e3 (sigma floored at 0.03), hence
+rtol 1e-4 / atol 2e-3 where the inputs themselves come from the device z-score."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import intree_oracle as I
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "intree_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def S():
+    from deepwmh_b200 import stage1
+    return stage1
+
+
+def h(t):
+    return t.cpu().numpy()
+
+
+def test_z_score_matches_reference_fixture(g, S):
+    z, st = S.z_score(g["in_target"], g["in_brain"], return_stats=True)
+    assert np.allclose(st[:2], g["masked_mean_std"], rtol=1e-6) and st[2] == (g["in_brain"] > 0.5).sum()
+    assert np.allclose(h(z), g["zscore_masked"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(S.z_score(g["in_target"])), g["zscore_plain"], rtol=1e-5, atol=1e-5)
+    # input untouched, numpy or tensor
+    t = torch.from_numpy(g["in_target"]).cuda()
+    S.z_score(t, g["in_brain"])
+    assert np.array_equal(h(t), g["in_target"])
+    filled = h(S.z_score(g["in_target"], g["in_brain"], fill_outside=True))
+    assert np.allclose(filled, g["pipe_x_prime"], rtol=1e-5, atol=1e-5)
+    with pytest.raises(Exception):
+        S.z_score(g["in_target"], None, fill_outside=True)
+
+
+def test_group_statistics_and_nll_match_reference_fixture(g, S):
+    zt, zr = g["z_target"], list(g["z_refs"])
+    assert np.allclose(h(S.group_mean(zr)), g["group_mean"], rtol=1e-6, atol=1e-6)
+    assert np.allclose(h(S.group_std(zr)), g["group_std"], rtol=1e-5, atol=1e-6)
+    for side, tag in ((None, "none"), ("+", "pos"), ("-", "neg")):
+        an, mu, sg = S.nll(zt, zr, min_std=0.03, side=side, return_all=True)
+        assert np.allclose(h(an), g["nll_" + tag], rtol=1e-4, atol=1e-4), tag
+    assert np.allclose(h(mu), g["nll_mu"], rtol=1e-6, atol=1e-6)
+    assert np.allclose(h(sg), g["nll_sigma"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(h(S.nll(zt, zr)), g["nll_eps"], rtol=1e-4, atol=1e-4)
+    an_m = S.nll(zt, zr, min_std=0.03, side="+", mul_mask=g["in_valid"])
+    assert np.allclose(h(an_m), g["nll_pos"] * g["in_valid"], rtol=1e-4, atol=1e-4)
+    with pytest.raises(NotImplementedError):
+        S.nll(zt, zr, use_mask=True)
+    with pytest.raises(AssertionError):
+        S.nll(zt, zr, side="x")
+    with pytest.raises(Exception):
+        S.nll(zt, [zr[0]] * 33)                                      # more references than the kernel's pointer table
+
+
+@pytest.mark.parametrize("tag", ["p12", "p50", "podd", "nomask"])
+def test_mean_std_grid_matches_reference_fixture(g, S, tag):
+    if tag == "nomask":
+        m, s = S.mean_std_grid(g["z_target"], [12, 12, 12])
+    else:
+        m, s = S.mean_std_grid(g["z_target"], g["msg_patch_" + tag].tolist(), mask=g["in_valid"])
+    assert np.allclose(h(m), g["msg_mean_" + tag], rtol=1e-5, atol=2e-6)
+    assert np.allclose(h(s), g["msg_std_" + tag], rtol=1e-5, atol=2e-6)
+    with pytest.raises(NotImplementedError):
+        S.mean_std_grid(g["z_target"], [12, 12, 12], order=3)
+
+
+@pytest.mark.parametrize("tag", ["iso1", "iso07", "mixed", "thick"])
+def test_median_3mm_bit_exact_with_reference_fixture(g, S, tag):
+    vox = g["median_vox_" + tag].tolist()
+    assert S.median_kernel_size(vox) == I.median_kernel(vox)
+    assert np.array_equal(h(S.median_3mm(g["nll_pos"], vox)), g["median_" + tag])
+
+
+def test_median_filter_edge_cases(S):
+    rng = np.random.default_rng(3)
+    for shape, ks in (((1, 1, 1), [3, 3, 3]), ((5, 3, 70), [1, 1, 1]), ((7, 9, 33), [9, 2, 5]), ((2, 70, 3), [3, 7, 1])):
+        x = rng.normal(size=shape).astype(np.float32)
+        x[rng.random(shape) > 0.7] = 0.0                              # ties with the zero padding
+        x[rng.random(shape) > 0.9] *= -1.0
+        from scipy.ndimage import median_filter
+        assert np.array_equal(h(S.median_filter(x, ks)), median_filter(x, size=ks, mode="constant", cval=0)), (shape, ks)
+    with pytest.raises(Exception):
+        S.median_filter(np.zeros((4, 4, 4), np.float32), [11, 3, 3])
+
+
+def test_anomaly_pipeline_matches_reference_fixture(g, S):
+    r = S.nll_anomaly_map(g["in_target"], list(g["in_refs"]), g["in_brain"], g["in_valid"], intensity_prior="+",
+                          image_patch=g["pipe_patch"].tolist(), with_reference_scores=True)
+    assert np.allclose(h(r["normalized_input"]), g["pipe_x_prime"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(r["local_mean"]), g["pipe_local_mu"] * g["in_valid"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(r["mean"]), g["pipe_mean"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(r["std"]), g["pipe_std"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(h(r["anomaly"]), g["pipe_anomaly"], rtol=1e-4, atol=2e-3)
+    assert np.allclose(h(r["reference_anomalies"][0]), g["pipe_ref_anomaly0"], rtol=1e-4, atol=2e-3)
+    # the lesion planted in the fixture's target is what the map finds
+    assert np.unravel_index(np.argmax(h(r["anomaly"])), g["in_target"].shape)[0] in range(12, 16)
+
+
+def test_full_size_volume_against_oracle(S):
+    """BASELINE.json's 182x218x182 shape, 1 mm isotropic: 50-voxel local-mean patch, 3x3x3 median."""
+    import oracle as O
+    shape = (182, 218, 182)
+    tgt = O.synthetic_flair(shape, seed=0)[0]
+    refs = [O.synthetic_flair(shape, seed=s)[0] for s in (1, 2, 3)]
+    brain = (tgt != 0).astype(np.float32)
+    valid = (brain * (np.random.default_rng(0).random(shape) > 0.05)).astype(np.float32)
+    r = S.nll_anomaly_map(tgt, refs, brain, valid, physical_voxel_size=[1.0, 1.0, 1.0], intensity_prior="+")
+    o = I.nll_anomaly_arrays(tgt, refs, brain, valid, S.image_patch_size([1.0, 1.0, 1.0]))
+    assert np.allclose(h(r["normalized_input"]), o["x_prime"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(r["local_mean"]), o["local_mu"] * valid, rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(r["mean"]), o["mean"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(r["std"]), o["std"], rtol=1e-4, atol=1e-5)
+    assert np.allclose(h(r["anomaly"]), o["anomaly"], rtol=1e-4, atol=2e-3)
+    an32 = h(r["anomaly"])
+    assert np.array_equal(h(S.median_3mm(an32, [1.0, 1.0, 1.0])), I.median_3mm(an32, [1.0, 1.0, 1.0]))
+    # size-independent properties: z-scored statistics over the mask, constant fill outside, NLL floor
+    z = h(r["normalized_input"])
+    inside = z[brain > 0.5].astype(np.float64)
+    assert abs(inside.mean()) < 1e-5 and abs(inside.std() - 1.0) < 1e-5
+    assert np.unique(z[brain < 0.5]).size == 1 and z[brain < 0.5][0] == np.float32(inside.min())
+    assert (h(r["std"]) >= np.float32(0.03)).all() and (an32[valid < 0.5] == 0).all()
