@@ -201,16 +201,18 @@ __global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ acc, cons
 }
 
 // checkpoint ensemble of masked background probabilities (deepwmh/pipeline/DCNN_multistage.py:102-125).
-//   y = 1 - m (1 - x)            per checkpoint, float64 arithmetic rounded to the float32 it is stored as (:108-109)
-//   field += y                    float32 field + float64 file values, rounded to float32 per step (:115-117)
+//   y = 1 - m (1 - x)            per checkpoint, float32 arrays (load_nifti_simple), one rounding per operation (:108-109)
+//   field += y                    float32 running field (:115-117)
 // and after the k checkpoints: field /= k; label = field < 0.5 (:118-119).
 __global__ void __launch_bounds__(256) ensemble_masked_add_kernel(float* __restrict__ acc, const float* __restrict__ x,
                                                                   const float* __restrict__ m, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const double mv = m ? (double)m[i] : 1.0;
-    const float y = (float)(1.0 - mv * (1.0 - (double)x[i]));
-    acc[i] = (float)((double)acc[i] + (double)y);
+    // float32 arithmetic, one rounding per operation, as numpy evaluates 1-(m*(1-x)) on the float32 arrays that
+    // load_nifti_simple returns (deepwmh/utilities/data_io.py:288-290); no FMA contraction
+    const float mv = m ? m[i] : 1.f;
+    const float y = __fsub_rn(1.f, __fmul_rn(mv, __fsub_rn(1.f, x[i])));
+    acc[i] = __fadd_rn(acc[i], y);
   }
 }
 __global__ void __launch_bounds__(256) ensemble_refine_kernel(float* __restrict__ acc, float k, uint8_t* __restrict__ label, int64_t n) {

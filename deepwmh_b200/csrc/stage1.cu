@@ -10,6 +10,7 @@
 #include "../../include/deepwmh_b200.h"
 
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
 
@@ -45,12 +46,23 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 // z_score.  ws: double[4] = {sum, sumsq, count, -} + int min (ordered) at byte 32.  Pass 1 reads x (+mask), pass 2
 // reads x (+mask) and writes x: 12 B/voxel (+8 with a mask).
 // ---------------------------------------------------------------------------------------------------------------
+template <bool VEC>
 __global__ void __launch_bounds__(256) s1_stats_kernel(const float* __restrict__ x, const float* __restrict__ mask,
                                                        int64_t n, double* __restrict__ acc, int* __restrict__ minord) {
   double s = 0.0, ss = 0.0, cnt = 0.0;
   int mn = 0x7fffffff;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = VEC ? n >> 2 : 0;
+  for (int64_t i = tid; i < n4; i += stride) {
+    const float4 v = dwmh::ld_stream_f4(reinterpret_cast<const float4*>(x) + i);
+    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (mask) m = dwmh::ld_stream_f4(reinterpret_cast<const float4*>(mask) + i);
+    const float vv[4] = {v.x, v.y, v.z, v.w}, mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (mm[j] > 0.5f) { s += vv[j]; ss += (double)vv[j] * vv[j]; cnt += 1.0; mn = min(mn, f2ord(vv[j])); }
+  }
+  for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
     const float v = x[i];
     if (!mask || mask[i] > 0.5f) { s += v; ss += (double)v * v; cnt += 1.0; mn = min(mn, f2ord(v)); }
   }
@@ -68,6 +80,7 @@ __global__ void __launch_bounds__(256) s1_stats_kernel(const float* __restrict__
   }
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(256) s1_zscore_apply_kernel(float* __restrict__ x, const float* __restrict__ mask, int64_t n,
                                                               const double* __restrict__ acc, const int* __restrict__ minord,
                                                               int fill_outside) {
@@ -77,10 +90,22 @@ __global__ void __launch_bounds__(256) s1_zscore_apply_kernel(float* __restrict_
   var = var > 0.0 ? var : 0.0;
   const double sd = fmax(sqrt(var), 0.00001);                       // np.max([std, 1e-5])
   const float fill = (float)(((double)ord2f(*minord) - mean) / sd);   // z-scoring is monotone: min(z) = z(min)
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  const bool do_fill = fill_outside && mask;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = VEC ? n >> 2 : 0;
+  for (int64_t i = tid; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (do_fill) m = dwmh::ld_stream_f4(reinterpret_cast<const float4*>(mask) + i);
+    v.x = m.x >= 0.5f ? (float)(((double)v.x - mean) / sd) : fill;    // np.where(m < 0.5, tissue_min, x)
+    v.y = m.y >= 0.5f ? (float)(((double)v.y - mean) / sd) : fill;
+    v.z = m.z >= 0.5f ? (float)(((double)v.z - mean) / sd) : fill;
+    v.w = m.w >= 0.5f ? (float)(((double)v.w - mean) / sd) : fill;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
     const float z = (float)(((double)x[i] - mean) / sd);
-    x[i] = (fill_outside && mask && !(mask[i] >= 0.5f)) ? fill : z;   // np.where(m < 0.5, tissue_min, x)
+    x[i] = (do_fill && !(mask[i] >= 0.5f)) ? fill : z;
   }
 }
 
@@ -95,32 +120,43 @@ struct GridGeom {
   int st[3];            // step = patch / 2 (patch rounded up to even)
   int pad[3];           // padded shape (multiple of the patch)
   int g[3];             // cells per axis = pad / st = grid shape
+  double scale[3];      // scipy zoom coordinate scale (in - 1) / (out - 1) of the bordered grid
 };
 
+// One CTA per (cell-x, cell-y, x-plane): thread t owns the z coordinates t, t + 256, ..., so every iteration
+// reads one contiguous z-row of the volume (coalesced, 8 rows in flight) and a thread's running sums belong to ONE
+// z-cell; the per-z sums are then folded into the z-cells through shared memory and added to `cells`
+// (zeroed by the host) with a handful of fp64 atomics per CTA.
+constexpr int CS_SLAB = 1;          // x-planes per CTA
 __global__ void __launch_bounds__(256) s1_cell_sums_kernel(const float* __restrict__ x, const float* __restrict__ mask,
-                                                           GridGeom q, double* __restrict__ cells) {
-  const int cz = blockIdx.x % q.g[2], cy = (blockIdx.x / q.g[2]) % q.g[1], cx = blockIdx.x / (q.g[2] * q.g[1]);
-  const int x0 = cx * q.st[0], y0 = cy * q.st[1], z0 = cz * q.st[2];
-  const int nx = max(0, min(q.st[0], q.X - x0)), ny = max(0, min(q.st[1], q.Y - y0)), nz = max(0, min(q.st[2], q.Z - z0));
-  double s = 0.0, ss = 0.0, cnt = 0.0;
-  const int rows = nx * ny;
-  // a warp walks one z-row at a time: consecutive lanes read consecutive floats
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  for (int r = w; r < rows; r += 8) {
-    const int64_t base = ((int64_t)(x0 + r / ny) * q.Y + (y0 + r % ny)) * q.Z + z0;
-    for (int k = l; k < nz; k += 32) {
-      const float v = x[base + k];
-      if (!mask || mask[base + k] > 0.5f) { s += v; ss += (double)v * v; cnt += 1.0; }
+                                                           GridGeom q, int slabs, double* __restrict__ cells) {
+  extern __shared__ double zs[];    // [3][g2]
+  const int slab = blockIdx.x % slabs, cy = (blockIdx.x / slabs) % q.g[1], cx = blockIdx.x / (slabs * q.g[1]);
+  const int x0 = cx * q.st[0] + slab * CS_SLAB, x1 = min(min(x0 + CS_SLAB, (cx + 1) * q.st[0]), q.X);
+  const int y0 = cy * q.st[1], y1 = min(y0 + q.st[1], q.Y);
+  for (int i = threadIdx.x; i < 3 * q.g[2]; i += blockDim.x) zs[i] = 0.0;
+  __syncthreads();
+  for (int z = threadIdx.x; z < q.Z; z += 256) {
+    double s = 0.0, ss = 0.0, cnt = 0.0;
+    for (int xi = x0; xi < x1; ++xi) {
+      const float* px = x + ((int64_t)xi * q.Y + y0) * q.Z + z;
+      const float* pm = mask ? mask + ((int64_t)xi * q.Y + y0) * q.Z + z : nullptr;
+#pragma unroll 8
+      for (int yi = 0; yi < y1 - y0; ++yi) {
+        const float v = __ldg(px + (int64_t)yi * q.Z);
+        const bool m = !pm || __ldg(pm + (int64_t)yi * q.Z) > 0.5f;
+        if (m) { s += v; ss += (double)v * v; cnt += 1.0; }
+      }
+    }
+    if (cnt > 0.0) {
+      const int cz = z / q.st[2];
+      atomicAdd(&zs[cz], s); atomicAdd(&zs[q.g[2] + cz], ss); atomicAdd(&zs[2 * q.g[2] + cz], cnt);
     }
   }
-  s = warp_sum_d(s); ss = warp_sum_d(ss); cnt = warp_sum_d(cnt);
-  __shared__ double sh[3][8];
-  if (l == 0) { sh[0][w] = s; sh[1][w] = ss; sh[2][w] = cnt; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) { s += sh[0][i]; ss += sh[1][i]; cnt += sh[2][i]; }
-    double* o = cells + (size_t)blockIdx.x * 3;
-    o[0] = s; o[1] = ss; o[2] = cnt;
+  for (int i = threadIdx.x; i < 3 * q.g[2]; i += blockDim.x) {
+    const int cz = i % q.g[2], w = i / q.g[2];
+    if (zs[i] != 0.0) atomicAdd(cells + ((size_t)(cx * q.g[1] + cy) * q.g[2] + cz) * 3 + w, zs[i]);
   }
 }
 
@@ -151,39 +187,37 @@ __global__ void s1_grid_stats_kernel(const double* __restrict__ cells, GridGeom 
 }
 
 // scipy.ndimage.zoom(grid, step, order=1): output index o <-> input coordinate o * (in - 1) / (out - 1)
-__device__ __forceinline__ void zoom_coord(int v, int st, int g, int& i0, double& f) {
-  const int in = g + 2, out = in * st;
-  const double c = (double)(v + st / 2) * ((double)(in - 1) / (double)(out - 1));
+__device__ __forceinline__ void zoom_coord(int v, int st, int g, double scale, int& i0, double& f) {
+  const double c = (double)(v + st / 2) * scale;
   i0 = (int)floor(c);
   f = c - (double)i0;
-  if (i0 >= in - 1) { i0 = in - 2; f = 1.0; }
+  if (i0 >= g + 1) { i0 = g; f = 1.0; }
 }
 
+// grid (X, ceil(Y / 8)), block 8 y-rows x 32 z-lanes: the x / y weights are per thread constants, z runs coalesced
 __global__ void __launch_bounds__(256) s1_grid_zoom_kernel(const double* __restrict__ mean_grid, const double* __restrict__ std_grid,
                                                            GridGeom q, float* __restrict__ mean_out, float* __restrict__ std_out) {
-  const int64_t V = (int64_t)q.X * q.Y * q.Z;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int x = blockIdx.x, y = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (y >= q.Y) return;
   const int G1 = q.g[1] + 2, G2 = q.g[2] + 2;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < V; t += stride) {
-    const int z = (int)(t % q.Z), y = (int)((t / q.Z) % q.Y), x = (int)(t / ((int64_t)q.Z * q.Y));
-    int i0, j0, k0; double fx, fy, fz;
-    zoom_coord(x, q.st[0], q.g[0], i0, fx); zoom_coord(y, q.st[1], q.g[1], j0, fy); zoom_coord(z, q.st[2], q.g[2], k0, fz);
-    const size_t o = ((size_t)i0 * G1 + j0) * G2 + k0;
-    const double w[2][2][2] = {{{(1 - fx) * (1 - fy) * (1 - fz), (1 - fx) * (1 - fy) * fz}, {(1 - fx) * fy * (1 - fz), (1 - fx) * fy * fz}},
-                               {{fx * (1 - fy) * (1 - fz), fx * (1 - fy) * fz}, {fx * fy * (1 - fz), fx * fy * fz}}};
+  int i0, j0; double fx, fy;
+  zoom_coord(x, q.st[0], q.g[0], q.scale[0], i0, fx); zoom_coord(y, q.st[1], q.g[1], q.scale[1], j0, fy);
+  const double wxy[4] = {(1 - fx) * (1 - fy), (1 - fx) * fy, fx * (1 - fy), fx * fy};
+  const size_t o4[4] = {((size_t)i0 * G1 + j0) * G2, ((size_t)i0 * G1 + j0 + 1) * G2, ((size_t)(i0 + 1) * G1 + j0) * G2,
+                        ((size_t)(i0 + 1) * G1 + j0 + 1) * G2};
+  const int64_t row = ((int64_t)x * q.Y + y) * q.Z;
+  for (int z = lane; z < q.Z; z += 32) {
+    int k0; double fz;
+    zoom_coord(z, q.st[2], q.g[2], q.scale[2], k0, fz);
     double m = 0.0, s = 0.0;
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const size_t p = o + ((size_t)a * G1 + b) * G2 + c;
-          m += w[a][b][c] * mean_grid[p];
-          if (std_out) s += w[a][b][c] * std_grid[p];
-        }
-    mean_out[t] = (float)m;
-    if (std_out) std_out[t] = (float)s;
+    for (int a = 0; a < 4; ++a) {
+      const double w0 = wxy[a] * (1 - fz), w1 = wxy[a] * fz;
+      m += w0 * mean_grid[o4[a] + k0] + w1 * mean_grid[o4[a] + k0 + 1];
+      if (std_out) s += w0 * std_grid[o4[a] + k0] + w1 * std_grid[o4[a] + k0 + 1];
+    }
+    mean_out[row + z] = (float)m;
+    if (std_out) std_out[row + z] = (float)s;
   }
 }
 
@@ -201,27 +235,57 @@ __global__ void __launch_bounds__(256) s1_align_kernel(float* __restrict__ x, co
 constexpr int S1_MAX_REFS = 32;
 struct RefPtrs { const float* p[S1_MAX_REFS]; };
 
-__global__ void __launch_bounds__(256) s1_group_nll_kernel(const float* __restrict__ xp, RefPtrs refs, int K, double min_std, int side,
+// Statistics are accumulated on the deviations from the first reference (exact in fp64 for fp32 data): identical
+// references give sigma == 0 exactly, as numpy's two-pass std does, and every reference value is read once.
+struct NllParams { double min_std; int side; int K; };
+__device__ __forceinline__ void nll_finish(double x, double r0, double sd, double sdd, const NllParams& q, float mul,
+                                           float& an, float& mu_f, float& sg_f) {
+  const double dm = sd / q.K, mu = r0 + dm;
+  double var = sdd / q.K - dm * dm;
+  var = var > 0.0 ? var : 0.0;
+  double sg = sqrt(var);
+  sg = q.min_std < 0.0 ? sg + 1e-6 : (sg < q.min_std ? q.min_std : sg);
+  double a = (x - mu) * (x - mu) / (2.0 * sg * sg) + log(sg * 2.506);
+  if (a != a) a = 0.0;                                                // np.nan_to_num(nan=0.0)
+  if (q.side > 0) a = x > mu ? a : 0.0;
+  else if (q.side < 0) a = x < mu ? a : 0.0;
+  an = (float)(a * (double)mul); mu_f = (float)mu; sg_f = (float)sg;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) s1_group_nll_kernel(const float* __restrict__ xp, RefPtrs refs, NllParams q,
                                                            const float* __restrict__ mul_mask, float* __restrict__ anomaly,
                                                            float* __restrict__ mu_out, float* __restrict__ sigma_out, int64_t n) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double s = 0.0;
-    for (int k = 0; k < K; ++k) s += (double)__ldg(refs.p[k] + i);
-    const double mu = s / K;
-    double v = 0.0;
-    for (int k = 0; k < K; ++k) { const double d = (double)__ldg(refs.p[k] + i) - mu; v += d * d; }   // second read hits L1/L2
-    double sg = sqrt(v / K);
-    sg = min_std < 0.0 ? sg + 1e-6 : (sg < min_std ? min_std : sg);
-    const double x = (double)xp[i];
-    double a = (x - mu) * (x - mu) / (2.0 * sg * sg) + log(sg * 2.506);
-    if (a != a) a = 0.0;                                              // np.nan_to_num(nan=0.0)
-    if (side > 0) a = x > mu ? a : 0.0;
-    else if (side < 0) a = x < mu ? a : 0.0;
-    if (mul_mask) a *= (double)mul_mask[i];
-    if (anomaly) anomaly[i] = (float)a;
-    if (mu_out) mu_out[i] = (float)mu;
-    if (sigma_out) sigma_out[i] = (float)sg;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = VEC ? n >> 2 : 0;
+  for (int64_t i = tid; i < n4; i += stride) {                        // 128-bit path: 4 voxels per thread
+    const float4 r0 = dwmh::ld_stream_f4(reinterpret_cast<const float4*>(refs.p[0]) + i);
+    double sd[4] = {0, 0, 0, 0}, sdd[4] = {0, 0, 0, 0};
+    for (int k = 1; k < q.K; ++k) {
+      const float4 r = dwmh::ld_stream_f4(reinterpret_cast<const float4*>(refs.p[k]) + i);
+      const double d0 = (double)r.x - (double)r0.x, d1 = (double)r.y - (double)r0.y, d2 = (double)r.z - (double)r0.z, d3 = (double)r.w - (double)r0.w;
+      sd[0] += d0; sdd[0] += d0 * d0; sd[1] += d1; sdd[1] += d1 * d1; sd[2] += d2; sdd[2] += d2 * d2; sd[3] += d3; sdd[3] += d3 * d3;
+    }
+    const float4 x = reinterpret_cast<const float4*>(xp)[i];
+    float4 m = make_float4(1.f, 1.f, 1.f, 1.f), an, mu, sg;
+    if (mul_mask) m = reinterpret_cast<const float4*>(mul_mask)[i];
+    nll_finish(x.x, r0.x, sd[0], sdd[0], q, m.x, an.x, mu.x, sg.x);
+    nll_finish(x.y, r0.y, sd[1], sdd[1], q, m.y, an.y, mu.y, sg.y);
+    nll_finish(x.z, r0.z, sd[2], sdd[2], q, m.z, an.z, mu.z, sg.z);
+    nll_finish(x.w, r0.w, sd[3], sdd[3], q, m.w, an.w, mu.w, sg.w);
+    if (anomaly) reinterpret_cast<float4*>(anomaly)[i] = an;
+    if (mu_out) reinterpret_cast<float4*>(mu_out)[i] = mu;
+    if (sigma_out) reinterpret_cast<float4*>(sigma_out)[i] = sg;
+  }
+  for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {             // scalar path / tail
+    const double r0 = (double)__ldg(refs.p[0] + i);
+    double sd = 0.0, sdd = 0.0;
+    for (int k = 1; k < q.K; ++k) { const double d = (double)__ldg(refs.p[k] + i) - r0; sd += d; sdd += d * d; }
+    float an, mu, sg;
+    nll_finish((double)xp[i], r0, sd, sdd, q, mul_mask ? mul_mask[i] : 1.f, an, mu, sg);
+    if (anomaly) anomaly[i] = an;
+    if (mu_out) mu_out[i] = mu;
+    if (sigma_out) sigma_out[i] = sg;
   }
 }
 
@@ -268,6 +332,56 @@ __global__ void __launch_bounds__(256) s1_median_kernel(const float* __restrict_
   out[((int64_t)gx * Y + gy) * Z + gz] = key2f(key);
 }
 
+// Compile-time odd windows up to 27 values (3x3x3 = the 1 mm isotropic case; 3x3 slices for thick-slice data): the
+// window goes through registers once and the median is found by forgetful selection -- of N/2 + 2 values neither the
+// minimum nor the maximum can be the median, so drop both, add the next value, repeat -- with min/max exchanges only
+// (~155 exchanges for N = 27 instead of 32 x 27 compares).
+template <int S, int W>
+__device__ __forceinline__ void minmax_ends(uint32_t (&v)[W]) {     // min of v[0..S) -> v[0], max -> v[S-1]
+#pragma unroll
+  for (int i = 0; i < S / 2; ++i) { const uint32_t lo = min(v[i], v[S - 1 - i]), hi = max(v[i], v[S - 1 - i]); v[i] = lo; v[S - 1 - i] = hi; }
+#pragma unroll
+  for (int i = 1; i <= (S - 1) / 2; ++i) { const uint32_t lo = min(v[0], v[i]), hi = max(v[0], v[i]); v[0] = lo; v[i] = hi; }
+#pragma unroll
+  for (int i = S / 2; i < S - 1; ++i) { const uint32_t lo = min(v[i], v[S - 1]), hi = max(v[i], v[S - 1]); v[i] = lo; v[S - 1] = hi; }
+}
+template <int S, int W, int N, int KY, int KZ>
+__device__ __forceinline__ void forget_step(uint32_t (&v)[W], const uint32_t* __restrict__ base, int ty, int tz) {
+  if constexpr (S >= 3) {
+    constexpr int e = N - (S - 2);                                   // index of the window value added at this size
+    if constexpr (S < W) v[0] = base[((e / (KY * KZ)) * ty + (e / KZ) % KY) * tz + e % KZ];
+    minmax_ends<S, W>(v);
+    forget_step<S - 1, W, N, KY, KZ>(v, base, ty, tz);
+  }
+}
+
+template <int KX, int KY, int KZ>
+__global__ void __launch_bounds__(256) s1_median_small_kernel(const float* __restrict__ in, float* __restrict__ out, int X, int Y, int Z) {
+  constexpr int N = KX * KY * KZ, W = N / 2 + 2;
+  static_assert(N % 2 == 1 && N >= 3 && N <= 27, "odd windows of 3..27 values");
+  constexpr int tx = MT_X + KX - 1, ty = MT_Y + KY - 1, tz = MT_Z + KZ - 1;
+  __shared__ uint32_t tile[tx * ty * tz];
+  const int bz = blockIdx.x * MT_Z, by = blockIdx.y * MT_Y, bx = blockIdx.z * MT_X;
+  const int ox = bx - KX / 2, oy = by - KY / 2, oz = bz - KZ / 2;
+  for (int t = threadIdx.x; t < tx * ty * tz; t += 256) {
+    const int c = t % tz, b = (t / tz) % ty, a = t / (tz * ty);
+    const int gx = ox + a, gy = oy + b, gz = oz + c;
+    float v = 0.f;
+    if (gx >= 0 && gx < X && gy >= 0 && gy < Y && gz >= 0 && gz < Z) v = in[((int64_t)gx * Y + gy) * Z + gz];
+    tile[t] = f2key(v);
+  }
+  __syncthreads();
+  const int lz = threadIdx.x % MT_Z, ly = (threadIdx.x / MT_Z) % MT_Y, lx = threadIdx.x / (MT_Z * MT_Y);
+  const int gx = bx + lx, gy = by + ly, gz = bz + lz;
+  if (gx >= X || gy >= Y || gz >= Z) return;
+  const uint32_t* base = tile + (lx * ty + ly) * tz + lz;
+  uint32_t v[W];
+#pragma unroll
+  for (int e = 0; e < W; ++e) v[e] = base[((e / (KY * KZ)) * ty + (e / KZ) % KY) * tz + e % KZ];
+  forget_step<W, W, N, KY, KZ>(v, base, ty, tz);                     // ends with the median of the last three in v[1]
+  out[((int64_t)gx * Y + gy) * Z + gz] = key2f(v[1]);
+}
+
 int geom(int X, int Y, int Z, const int32_t patch[3], GridGeom* q) {
   if (X <= 0 || Y <= 0 || Z <= 0) return fail("mean_std_grid: empty volume");
   q->X = X; q->Y = Y; q->Z = Z;
@@ -278,6 +392,7 @@ int geom(int X, int Y, int Z, const int32_t patch[3], GridGeom* q) {
     q->st[a] = ps / 2;
     q->pad[a] = ps * ((sh[a] + ps - 1) / ps);
     q->g[a] = q->pad[a] / q->st[a];
+    q->scale[a] = (double)(q->g[a] + 1) / (double)((q->g[a] + 2) * q->st[a] - 1);
   }
   return 0;
 }
@@ -295,10 +410,15 @@ extern "C" int dwmh_s1_zscore(int32_t device, float* x, const float* mask, int64
   double* acc = (double*)workspace;
   int* mn = (int*)((char*)workspace + 32);
   S1_CU(cudaMemsetAsync(workspace, 0, 32, st));
-  S1_CU(cudaMemsetAsync(mn, 0x7f, 4, st));                           // 0x7f7f7f7f: above every finite float's key
+  S1_CU(cudaMemsetAsync(mn, 0x7f, 4, st));                           // 0x7f7f7f7f: above the key of every float below 3.39e38
   const int grid = grid_for(device);
-  s1_stats_kernel<<<grid, 256, 0, st>>>(x, mask, n, acc, mn);
-  s1_zscore_apply_kernel<<<grid, 256, 0, st>>>(x, mask, n, acc, mn, fill_outside);
+  if ((((uintptr_t)x | (uintptr_t)mask) & 15) == 0) {
+    s1_stats_kernel<true><<<grid, 256, 0, st>>>(x, mask, n, acc, mn);
+    s1_zscore_apply_kernel<true><<<grid, 256, 0, st>>>(x, mask, n, acc, mn, fill_outside);
+  } else {
+    s1_stats_kernel<false><<<grid, 256, 0, st>>>(x, mask, n, acc, mn);
+    s1_zscore_apply_kernel<false><<<grid, 256, 0, st>>>(x, mask, n, acc, mn, fill_outside);
+  }
   S1_CU(cudaGetLastError());
   if (stats_out) {
     double h[4];
@@ -331,10 +451,13 @@ extern "C" int dwmh_s1_mean_std_grid(int32_t device, const float* x, const float
   double* cells = (double*)workspace;
   double* mg = (double*)((char*)workspace + align256(ncell * 3 * sizeof(double)));
   double* sg = (double*)((char*)mg + align256(ngrid * sizeof(double)));
-  S1_CU(cudaMemsetAsync(mg, 0, 2 * align256(ngrid * sizeof(double)), st));
-  s1_cell_sums_kernel<<<(unsigned)ncell, 256, 0, st>>>(x, mask, q, cells);
+  S1_CU(cudaMemsetAsync(workspace, 0, align256(ncell * 3 * sizeof(double)) + 2 * align256(ngrid * sizeof(double)), st));
+  const int slabs = (q.st[0] + CS_SLAB - 1) / CS_SLAB;
+  if (3 * q.g[2] * sizeof(double) > 40000) return fail("dwmh_s1_mean_std_grid: %d cells along z exceed the shared-memory table", q.g[2]);
+  s1_cell_sums_kernel<<<(unsigned)(q.g[0] * q.g[1] * slabs), 256, 3 * q.g[2] * sizeof(double), st>>>(x, mask, q, slabs, cells);
   s1_grid_stats_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(cells, q, mask ? 1 : 0, mg, sg);
-  s1_grid_zoom_kernel<<<grid_for(device), 256, 0, st>>>(mg, sg, q, mean_out, std_out);
+  if ((Y + 7) / 8 > 65535) return fail("dwmh_s1_mean_std_grid: volume too large");
+  s1_grid_zoom_kernel<<<dim3(X, (Y + 7) / 8), 256, 0, st>>>(mg, sg, q, mean_out, std_out);
   S1_CU(cudaGetLastError());
   return 0;
 }
@@ -355,7 +478,11 @@ extern "C" int dwmh_s1_group_nll(int32_t device, const float* x_prime, const flo
   RefPtrs rp{};
   for (int i = 0; i < k; ++i) { if (!refs[i]) return fail("dwmh_s1_group_nll: refs[%d] is null", i); rp.p[i] = refs[i]; }
   S1_CU(cudaSetDevice(device));
-  s1_group_nll_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x_prime, rp, k, min_std, side, mul_mask, anomaly, mu_out, sigma_out, n);
+  uintptr_t al = (uintptr_t)x_prime | (uintptr_t)mul_mask | (uintptr_t)anomaly | (uintptr_t)mu_out | (uintptr_t)sigma_out;
+  for (int i = 0; i < k; ++i) al |= (uintptr_t)refs[i];
+  const NllParams q{min_std, side, k};
+  if ((al & 15) == 0) s1_group_nll_kernel<true><<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x_prime, rp, q, mul_mask, anomaly, mu_out, sigma_out, n);
+  else s1_group_nll_kernel<false><<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x_prime, rp, q, mul_mask, anomaly, mu_out, sigma_out, n);
   S1_CU(cudaGetLastError());
   return 0;
 }
@@ -371,7 +498,12 @@ extern "C" int dwmh_s1_median_filter(int32_t device, const float* in, float* out
   const size_t smem = (size_t)(MT_X + kx - 1) * (MT_Y + ky - 1) * (MT_Z + kz - 1) * sizeof(uint32_t);
   dim3 grid((Z + MT_Z - 1) / MT_Z, (Y + MT_Y - 1) / MT_Y, (X + MT_X - 1) / MT_X);
   if (grid.y > 65535 || grid.z > 65535) return fail("dwmh_s1_median_filter: volume too large");
-  s1_median_kernel<<<grid, 256, smem, (cudaStream_t)stream_>>>(in, out, X, Y, Z, kx, ky, kz);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (kx == 3 && ky == 3 && kz == 3) s1_median_small_kernel<3, 3, 3><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
+  else if (kx == 1 && ky == 3 && kz == 3) s1_median_small_kernel<1, 3, 3><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
+  else if (kx == 3 && ky == 1 && kz == 3) s1_median_small_kernel<3, 1, 3><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
+  else if (kx == 3 && ky == 3 && kz == 1) s1_median_small_kernel<3, 3, 1><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
+  else s1_median_kernel<<<grid, 256, smem, st>>>(in, out, X, Y, Z, kx, ky, kz);
   S1_CU(cudaGetLastError());
   return 0;
 }

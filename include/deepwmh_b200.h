@@ -101,7 +101,7 @@ int dwmh_argmax2(dwmh_ctx* ctx, const float* softmax_dev, uint8_t* seg_dev, int6
 
 /* --- checkpoint ensemble with softmax masking (deepwmh/pipeline/DCNN_multistage.py:102-125,317-394).
  * dwmh_ensemble_masked_add: acc += 1 - m (1 - x) for one checkpoint's BACKGROUND probability x (the fork's
- * `<case>_0.nii.gz`), valid mask m (NULL = all ones), with the reference's rounding (float64 arithmetic, float32 storage).
+ * `<case>_0.nii.gz`), valid mask m (NULL = all ones), with the reference's rounding (float32 arrays from load_nifti_simple: one rounding per operation).
  * dwmh_ensemble_refine: acc /= k (the ensembled field, in place) and label = acc < 0.5 (label_dev may be NULL). */
 int dwmh_ensemble_masked_add(dwmh_ctx* ctx, float* acc_dev, const float* bg_softmax_dev, const float* valid_mask_dev,
                              int64_t n, void* stream);

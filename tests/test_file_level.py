@@ -182,20 +182,22 @@ def test_device_remove_sparks_matches_scipy_components():
         s[i, 15 if i % 2 == 0 else 0, :] = 2
     got = net.remove_sparks(torch.from_numpy(s).cuda(), 3).cpu().numpy()
     assert np.array_equal(got, preprocess.remove_sparks(s, 3).astype(np.uint8))
+    # outputs of the reference's own remove_sparks / remove_3mm_sparks (tests/golden/make_golden_intree.py)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "intree_v1.npz"))
+    sp = torch.from_numpy((g["sparks_in"] > 0.5).astype(np.uint8)).cuda()
+    for tag in ("iso1", "iso05", "iso2", "thick", "aniso"):
+        got = net.remove_3mm_sparks(sp, g["sparks_vox_" + tag].tolist()).cpu().numpy()
+        assert np.array_equal(got, g["sparks_" + tag]), tag
+    assert np.array_equal(net.remove_sparks(sp, 5).cpu().numpy(), g["sparks_min5"])
     net.close()
 
 
 def _ref_masked_ensemble(xs, m, voxel_size):
-    """numpy restatement of _parallel_softmax_masking + _parallel_ensembling (DCNN_multistage.py:102-125): float64 file
-    values (nibabel get_fdata) of float32 NIfTIs, float32 running field."""
-    field = np.zeros(xs[0].shape).astype("float32")
-    for x in xs:
-        y = 1 - (m.astype(np.float64) * (1 - x.astype(np.float64)))
-        y = y.astype(np.float32).astype(np.float64)               # saved as float32, loaded as float64
-        field += y
-    field = field / len(xs)
-    label = (field < 0.5).astype("float32")
-    return field, preprocess.remove_3mm_sparks(label, voxel_size).astype(np.uint8)
+    """numpy restatement of _parallel_softmax_masking + _parallel_ensembling (DCNN_multistage.py:102-125): float32 arrays
+    from load_nifti_simple (utilities/data_io.py:288-290), float32 running field; pinned by tests/test_intree_oracle.py."""
+    from oracle import intree_oracle as I
+    field, label = I.ensembling([I.softmax_masking(x, m) for x in xs], voxel_size)
+    return field, label.astype(np.uint8)
 
 
 @pytest.mark.gpu
@@ -221,6 +223,14 @@ def test_device_masked_ensemble_is_bit_exact():
         f_ref, l_ref = _ref_masked_ensemble(xs, mask if mask is not None else np.ones(shape, np.float32), [1.0, 1.0, 1.0])
         assert np.array_equal(acc.cpu().numpy(), f_ref)
         assert np.array_equal(clean.cpu().numpy(), l_ref)
+    # the reference's own two workers on seeded inputs (tests/golden/make_golden_intree.py)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "intree_v1.npz"))
+    acc = torch.zeros(g["ens_field"].shape, dtype=torch.float32, device="cuda")
+    md = torch.from_numpy(g["ens_mask"]).cuda()
+    for x in g["ens_x"]:
+        net.ensemble_masked_add_(acc, torch.from_numpy(x).cuda(), md)
+    label = net.remove_3mm_sparks(net.ensemble_refine_(acc, len(g["ens_x"])), [1.0, 1.0, 1.0])
+    assert np.array_equal(acc.cpu().numpy(), g["ens_field"]) and np.array_equal(label.cpu().numpy(), g["ens_label"])
     net.close()
 
 
