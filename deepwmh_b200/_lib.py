@@ -45,6 +45,10 @@ SYMBOLS = {
     "dwmh_ensemble_refine": (C.c_int, [_P, _P, C.c_int32, _P, C.c_int64, _P]),
     "dwmh_remove_sparks": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "dwmh_s1_zscore": (C.c_int, [C.c_int32, _P, _P, C.c_int64, C.c_int32, _P, C.POINTER(C.c_double), _P]),
+    "dwmh_s1_zscore_batch": (C.c_int, [C.c_int32, C.POINTER(_P), C.c_int32, _P, C.c_int64, C.c_int32, _P, _P]),
+    "dwmh_s1_local_mean_align_workspace": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int64)]),
+    "dwmh_s1_local_mean_align": (C.c_int, [C.c_int32, _P, C.POINTER(_P), C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32,
+                                           C.POINTER(C.c_int32), _P, _P, _P]),
     "dwmh_s1_mean_std_grid_workspace": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "dwmh_s1_mean_std_grid": (C.c_int, [C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P]),
     "dwmh_s1_align_local_mean": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P]),

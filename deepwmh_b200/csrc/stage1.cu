@@ -38,6 +38,12 @@ int grid_for(int device) {
 
 using dwmh::warp_sum_d;
 
+// Batched launches: blockIdx.y selects one of up to S1_MAX_VOLS volumes (the target + its registered references).
+constexpr int S1_MAX_REFS = 32;
+constexpr int S1_MAX_VOLS = S1_MAX_REFS + 1;
+struct VolPtrs { float* p[S1_MAX_VOLS]; };
+constexpr int ZS_SLOT = 8;          // doubles per volume in the z-score workspace: {sum, sumsq, count, -, min (int), ...}
+
 // order-preserving float <-> signed int (atomicMin on floats)
 __device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
@@ -47,8 +53,11 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 // reads x (+mask) and writes x: 12 B/voxel (+8 with a mask).
 // ---------------------------------------------------------------------------------------------------------------
 template <bool VEC>
-__global__ void __launch_bounds__(256) s1_stats_kernel(const float* __restrict__ x, const float* __restrict__ mask,
-                                                       int64_t n, double* __restrict__ acc, int* __restrict__ minord) {
+__global__ void __launch_bounds__(256) s1_stats_kernel(VolPtrs vols, const float* __restrict__ mask,
+                                                       int64_t n, double* __restrict__ ws) {
+  const float* __restrict__ x = vols.p[blockIdx.y];
+  double* acc = ws + (size_t)blockIdx.y * ZS_SLOT;
+  int* minord = reinterpret_cast<int*>(acc + 4);
   double s = 0.0, ss = 0.0, cnt = 0.0;
   int mn = 0x7fffffff;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,9 +90,11 @@ __global__ void __launch_bounds__(256) s1_stats_kernel(const float* __restrict__
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) s1_zscore_apply_kernel(float* __restrict__ x, const float* __restrict__ mask, int64_t n,
-                                                              const double* __restrict__ acc, const int* __restrict__ minord,
-                                                              int fill_outside) {
+__global__ void __launch_bounds__(256) s1_zscore_apply_kernel(VolPtrs vols, const float* __restrict__ mask, int64_t n,
+                                                              const double* __restrict__ ws, int fill_outside) {
+  float* __restrict__ x = vols.p[blockIdx.y];
+  const double* acc = ws + (size_t)blockIdx.y * ZS_SLOT;
+  const int* minord = reinterpret_cast<const int*>(acc + 4);
   const double cnt = acc[2] > 0.0 ? acc[2] : 1.0;
   const double mean = acc[0] / cnt;
   double var = acc[1] / cnt - mean * mean;
@@ -127,10 +138,12 @@ struct GridGeom {
 // reads one contiguous z-row of the volume (coalesced, 8 rows in flight) and a thread's running sums belong to ONE
 // z-cell; the per-z sums are then folded into the z-cells through shared memory and added to `cells`
 // (zeroed by the host) with a handful of fp64 atomics per CTA.
-constexpr int CS_SLAB = 1;          // x-planes per CTA
-__global__ void __launch_bounds__(256) s1_cell_sums_kernel(const float* __restrict__ x, const float* __restrict__ mask,
-                                                           GridGeom q, int slabs, double* __restrict__ cells) {
+constexpr int CS_SLAB = 5;          // x-planes per CTA
+__global__ void __launch_bounds__(256) s1_cell_sums_kernel(VolPtrs vols, const float* __restrict__ mask,
+                                                           GridGeom q, int slabs, double* __restrict__ cells_all) {
   extern __shared__ double zs[];    // [3][g2]
+  const float* __restrict__ x = vols.p[blockIdx.y];
+  double* cells = cells_all + (size_t)blockIdx.y * q.g[0] * q.g[1] * q.g[2] * 3;
   const int slab = blockIdx.x % slabs, cy = (blockIdx.x / slabs) % q.g[1], cx = blockIdx.x / (slabs * q.g[1]);
   const int x0 = cx * q.st[0] + slab * CS_SLAB, x1 = min(min(x0 + CS_SLAB, (cx + 1) * q.st[0]), q.X);
   const int y0 = cy * q.st[1], y1 = min(y0 + q.st[1], q.Y);
@@ -161,10 +174,13 @@ __global__ void __launch_bounds__(256) s1_cell_sums_kernel(const float* __restri
 }
 
 // grids: [g0+2][g1+2][g2+2] doubles, borders zero (memset by the host)
-__global__ void s1_grid_stats_kernel(const double* __restrict__ cells, GridGeom q, int masked,
-                                     double* __restrict__ mean_grid, double* __restrict__ std_grid) {
+__global__ void s1_grid_stats_kernel(const double* __restrict__ cells_all, GridGeom q, int masked,
+                                     double* __restrict__ mean_grids, double* __restrict__ std_grids, size_t grid_stride) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= q.g[0] * q.g[1] * q.g[2]) return;
+  const double* cells = cells_all + (size_t)blockIdx.y * q.g[0] * q.g[1] * q.g[2] * 3;
+  double* mean_grid = mean_grids + blockIdx.y * grid_stride;
+  double* std_grid = std_grids + blockIdx.y * grid_stride;
   const int k = t % q.g[2], j = (t / q.g[2]) % q.g[1], i = t / (q.g[2] * q.g[1]);
   double s = 0.0, ss = 0.0, cnt = 0.0;
   for (int a = i; a < min(i + 2, q.g[0]); ++a)                       // the last block is clipped by the padded shape
@@ -194,30 +210,38 @@ __device__ __forceinline__ void zoom_coord(int v, int st, int g, double scale, i
   if (i0 >= g + 1) { i0 = g; f = 1.0; }
 }
 
-// grid (X, ceil(Y / 8)), block 8 y-rows x 32 z-lanes: the x / y weights are per thread constants, z runs coalesced
+// Linear zoom is separable: for one (x, y) row the four x/y corner rows of the coarse grid collapse into ONE z-profile
+// prof[k] = sum_a wxy[a] * grid[corner_a][k] (G2 <= a few dozen values, built once per row by the warp), after which a voxel
+// needs two profile reads and one lerp instead of eight grid reads.
+__device__ __forceinline__ void row_profile(const double* __restrict__ grid, const size_t (&o4)[4], const double (&wxy)[4], int G2,
+                                            int lane, double* __restrict__ prof) {
+  for (int k = lane; k < G2; k += 32)
+    prof[k] = wxy[0] * grid[o4[0] + k] + wxy[1] * grid[o4[1] + k] + wxy[2] * grid[o4[2] + k] + wxy[3] * grid[o4[3] + k];
+}
+
+// grid (X, ceil(Y / 8)), block 8 y-rows x 32 z-lanes (one warp per row, z coalesced); dynamic smem 8 x 2 x G2 doubles
 __global__ void __launch_bounds__(256) s1_grid_zoom_kernel(const double* __restrict__ mean_grid, const double* __restrict__ std_grid,
                                                            GridGeom q, float* __restrict__ mean_out, float* __restrict__ std_out) {
-  const int x = blockIdx.x, y = blockIdx.y * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (y >= q.Y) return;
+  extern __shared__ double prof_all[];
+  const int x = blockIdx.x, w = threadIdx.x >> 5, y = blockIdx.y * 8 + w, lane = threadIdx.x & 31;
+  if (y >= q.Y) return;                                              // whole warp
   const int G1 = q.g[1] + 2, G2 = q.g[2] + 2;
+  double* pm = prof_all + (size_t)w * 2 * G2;
+  double* ps = pm + G2;
   int i0, j0; double fx, fy;
   zoom_coord(x, q.st[0], q.g[0], q.scale[0], i0, fx); zoom_coord(y, q.st[1], q.g[1], q.scale[1], j0, fy);
   const double wxy[4] = {(1 - fx) * (1 - fy), (1 - fx) * fy, fx * (1 - fy), fx * fy};
   const size_t o4[4] = {((size_t)i0 * G1 + j0) * G2, ((size_t)i0 * G1 + j0 + 1) * G2, ((size_t)(i0 + 1) * G1 + j0) * G2,
                         ((size_t)(i0 + 1) * G1 + j0 + 1) * G2};
+  row_profile(mean_grid, o4, wxy, G2, lane, pm);
+  if (std_out) row_profile(std_grid, o4, wxy, G2, lane, ps);
+  __syncwarp();
   const int64_t row = ((int64_t)x * q.Y + y) * q.Z;
   for (int z = lane; z < q.Z; z += 32) {
     int k0; double fz;
     zoom_coord(z, q.st[2], q.g[2], q.scale[2], k0, fz);
-    double m = 0.0, s = 0.0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const double w0 = wxy[a] * (1 - fz), w1 = wxy[a] * fz;
-      m += w0 * mean_grid[o4[a] + k0] + w1 * mean_grid[o4[a] + k0 + 1];
-      if (std_out) s += w0 * std_grid[o4[a] + k0] + w1 * std_grid[o4[a] + k0 + 1];
-    }
-    mean_out[row + z] = (float)m;
-    if (std_out) std_out[row + z] = (float)s;
+    mean_out[row + z] = (float)(pm[k0] * (1 - fz) + pm[k0 + 1] * fz);
+    if (std_out) std_out[row + z] = (float)(ps[k0] * (1 - fz) + ps[k0 + 1] * fz);
   }
 }
 
@@ -228,11 +252,40 @@ __global__ void __launch_bounds__(256) s1_align_kernel(float* __restrict__ x, co
     x[i] = (float)(((double)x[i] - (double)mu_i[i]) + (double)mu_p[i]);
 }
 
+// lesion_analysis.py:163-169 in one launch: blockIdx.z = 0 is the target (its zoomed local mean is written to mu_out,
+// if given), blockIdx.z >= 1 a reference, aligned in place: x_i = (x_i - zoom(grid_i)) + zoom(grid_target), evaluated from
+// the two coarse grids in fp64 -- the references' local-mean volumes are never materialised.
+__global__ void __launch_bounds__(256) s1_zoom_align_kernel(const double* __restrict__ mean_grids, size_t grid_stride, GridGeom q,
+                                                            VolPtrs vols, float* __restrict__ mu_out) {
+  extern __shared__ double prof_all[];
+  const int x = blockIdx.x, w = threadIdx.x >> 5, y = blockIdx.y * 8 + w, lane = threadIdx.x & 31, vol = blockIdx.z;
+  if (y >= q.Y || (vol == 0 && !mu_out)) return;                     // whole warp
+  const int G1 = q.g[1] + 2, G2 = q.g[2] + 2;
+  double* pt = prof_all + (size_t)w * 2 * G2;
+  double* pr = pt + G2;
+  int i0, j0; double fx, fy;
+  zoom_coord(x, q.st[0], q.g[0], q.scale[0], i0, fx); zoom_coord(y, q.st[1], q.g[1], q.scale[1], j0, fy);
+  const double wxy[4] = {(1 - fx) * (1 - fy), (1 - fx) * fy, fx * (1 - fy), fx * fy};
+  const size_t o4[4] = {((size_t)i0 * G1 + j0) * G2, ((size_t)i0 * G1 + j0 + 1) * G2, ((size_t)(i0 + 1) * G1 + j0) * G2,
+                        ((size_t)(i0 + 1) * G1 + j0 + 1) * G2};
+  row_profile(mean_grids, o4, wxy, G2, lane, pt);                    // target grid
+  if (vol) row_profile(mean_grids + (size_t)vol * grid_stride, o4, wxy, G2, lane, pr);
+  __syncwarp();
+  const int64_t row = ((int64_t)x * q.Y + y) * q.Z;
+  float* xr = vols.p[vol];
+  for (int z = lane; z < q.Z; z += 32) {
+    int k0; double fz;
+    zoom_coord(z, q.st[2], q.g[2], q.scale[2], k0, fz);
+    const double mt = pt[k0] * (1 - fz) + pt[k0 + 1] * fz;
+    if (vol == 0) mu_out[row + z] = (float)mt;
+    else xr[row + z] = (float)(((double)xr[row + z] - (pr[k0] * (1 - fz) + pr[k0 + 1] * fz)) + mt);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // group mean / population std over the K reference volumes + NLL of the target, one pass: (K + 1) x 4 B read,
 // 4 .. 12 B written per voxel.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int S1_MAX_REFS = 32;
 struct RefPtrs { const float* p[S1_MAX_REFS]; };
 
 // Statistics are accumulated on the deviations from the first reference (exact in fp64 for fp32 data): identical
@@ -400,6 +453,24 @@ size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
 
+static int zscore_launch(int device, VolPtrs vols, int nvol, const float* mask, int64_t n, int fill_outside, void* workspace,
+                         bool aligned, cudaStream_t st) {
+  double* ws = (double*)workspace;
+  S1_CU(cudaMemsetAsync(ws, 0, (size_t)nvol * ZS_SLOT * sizeof(double), st));
+  // min slot <- 0x7f7f7f7f (above the key of every float below 3.39e38): one strided 2-D memset over the slots
+  S1_CU(cudaMemset2DAsync((char*)workspace + 32, ZS_SLOT * sizeof(double), 0x7f, 4, nvol, st));
+  const dim3 grid((grid_for(device) + nvol - 1) / nvol, nvol);
+  if (aligned) {
+    s1_stats_kernel<true><<<grid, 256, 0, st>>>(vols, mask, n, ws);
+    s1_zscore_apply_kernel<true><<<grid, 256, 0, st>>>(vols, mask, n, ws, fill_outside);
+  } else {
+    s1_stats_kernel<false><<<grid, 256, 0, st>>>(vols, mask, n, ws);
+    s1_zscore_apply_kernel<false><<<grid, 256, 0, st>>>(vols, mask, n, ws, fill_outside);
+  }
+  S1_CU(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int dwmh_s1_zscore(int32_t device, float* x, const float* mask, int64_t n, int32_t fill_outside, void* workspace,
                               double* stats_out, void* stream_) {
   if (!x || !workspace) return fail("dwmh_s1_zscore: null argument");
@@ -407,28 +478,30 @@ extern "C" int dwmh_s1_zscore(int32_t device, float* x, const float* mask, int64
   if (fill_outside && !mask) return fail("dwmh_s1_zscore: fill_outside needs a mask");
   cudaStream_t st = (cudaStream_t)stream_;
   S1_CU(cudaSetDevice(device));
-  double* acc = (double*)workspace;
-  int* mn = (int*)((char*)workspace + 32);
-  S1_CU(cudaMemsetAsync(workspace, 0, 32, st));
-  S1_CU(cudaMemsetAsync(mn, 0x7f, 4, st));                           // 0x7f7f7f7f: above the key of every float below 3.39e38
-  const int grid = grid_for(device);
-  if ((((uintptr_t)x | (uintptr_t)mask) & 15) == 0) {
-    s1_stats_kernel<true><<<grid, 256, 0, st>>>(x, mask, n, acc, mn);
-    s1_zscore_apply_kernel<true><<<grid, 256, 0, st>>>(x, mask, n, acc, mn, fill_outside);
-  } else {
-    s1_stats_kernel<false><<<grid, 256, 0, st>>>(x, mask, n, acc, mn);
-    s1_zscore_apply_kernel<false><<<grid, 256, 0, st>>>(x, mask, n, acc, mn, fill_outside);
-  }
-  S1_CU(cudaGetLastError());
+  VolPtrs vols{}; vols.p[0] = x;
+  if (zscore_launch(device, vols, 1, mask, n, fill_outside, workspace, (((uintptr_t)x | (uintptr_t)mask) & 15) == 0, st)) return 1;
   if (stats_out) {
     double h[4];
-    S1_CU(cudaMemcpyAsync(h, acc, sizeof h, cudaMemcpyDeviceToHost, st));
+    S1_CU(cudaMemcpyAsync(h, workspace, sizeof h, cudaMemcpyDeviceToHost, st));
     S1_CU(cudaStreamSynchronize(st));
     const double cnt = h[2] > 0 ? h[2] : 1.0, m = h[0] / cnt;
     double var = h[1] / cnt - m * m; if (var < 0) var = 0;
     stats_out[0] = m; stats_out[1] = sqrt(var); stats_out[2] = h[2];
   }
   return 0;
+}
+
+extern "C" int dwmh_s1_zscore_batch(int32_t device, float* const* xs, int32_t nvol, const float* mask, int64_t n, int32_t fill_outside,
+                                    void* workspace, void* stream_) {
+  if (!xs || !workspace) return fail("dwmh_s1_zscore_batch: null argument");
+  if (nvol <= 0 || nvol > S1_MAX_VOLS) return fail("dwmh_s1_zscore_batch: %d volumes (1..%d supported)", nvol, S1_MAX_VOLS);
+  if (n <= 0) return fail("dwmh_s1_zscore_batch: empty volume");
+  if (fill_outside && !mask) return fail("dwmh_s1_zscore_batch: fill_outside needs a mask");
+  VolPtrs vols{};
+  uintptr_t al = (uintptr_t)mask;
+  for (int i = 0; i < nvol; ++i) { if (!xs[i]) return fail("dwmh_s1_zscore_batch: xs[%d] is null", i); vols.p[i] = xs[i]; al |= (uintptr_t)xs[i]; }
+  S1_CU(cudaSetDevice(device));
+  return zscore_launch(device, vols, nvol, mask, n, fill_outside, workspace, (al & 15) == 0, (cudaStream_t)stream_);
 }
 
 extern "C" int dwmh_s1_mean_std_grid_workspace(int32_t X, int32_t Y, int32_t Z, const int32_t patch_size[3], int64_t* bytes) {
@@ -453,11 +526,50 @@ extern "C" int dwmh_s1_mean_std_grid(int32_t device, const float* x, const float
   double* sg = (double*)((char*)mg + align256(ngrid * sizeof(double)));
   S1_CU(cudaMemsetAsync(workspace, 0, align256(ncell * 3 * sizeof(double)) + 2 * align256(ngrid * sizeof(double)), st));
   const int slabs = (q.st[0] + CS_SLAB - 1) / CS_SLAB;
-  if (3 * q.g[2] * sizeof(double) > 40000) return fail("dwmh_s1_mean_std_grid: %d cells along z exceed the shared-memory table", q.g[2]);
-  s1_cell_sums_kernel<<<(unsigned)(q.g[0] * q.g[1] * slabs), 256, 3 * q.g[2] * sizeof(double), st>>>(x, mask, q, slabs, cells);
-  s1_grid_stats_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(cells, q, mask ? 1 : 0, mg, sg);
+  if (q.g[2] > 300) return fail("dwmh_s1_mean_std_grid: %d cells along z exceed the shared-memory tables (300)", q.g[2]);
+  VolPtrs vols{}; vols.p[0] = const_cast<float*>(x);
+  s1_cell_sums_kernel<<<(unsigned)(q.g[0] * q.g[1] * slabs), 256, 3 * q.g[2] * sizeof(double), st>>>(vols, mask, q, slabs, cells);
+  s1_grid_stats_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(cells, q, mask ? 1 : 0, mg, sg, 0);
   if ((Y + 7) / 8 > 65535) return fail("dwmh_s1_mean_std_grid: volume too large");
-  s1_grid_zoom_kernel<<<dim3(X, (Y + 7) / 8), 256, 0, st>>>(mg, sg, q, mean_out, std_out);
+  s1_grid_zoom_kernel<<<dim3(X, (Y + 7) / 8), 256, 16 * (q.g[2] + 2) * sizeof(double), st>>>(mg, sg, q, mean_out, std_out);
+  S1_CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwmh_s1_local_mean_align_workspace(int32_t X, int32_t Y, int32_t Z, const int32_t patch_size[3], int32_t k, int64_t* bytes) {
+  GridGeom q;
+  if (!patch_size || !bytes) return fail("dwmh_s1_local_mean_align_workspace: null argument");
+  if (k < 0 || k > S1_MAX_REFS) return fail("dwmh_s1_local_mean_align_workspace: k = %d (0..%d supported)", k, S1_MAX_REFS);
+  if (geom(X, Y, Z, patch_size, &q)) return 1;
+  const size_t cells = (size_t)q.g[0] * q.g[1] * q.g[2], grid = (size_t)(q.g[0] + 2) * (q.g[1] + 2) * (q.g[2] + 2);
+  *bytes = (int64_t)(align256((size_t)(k + 1) * cells * 3 * sizeof(double)) + 2 * (size_t)(k + 1) * align256(grid * sizeof(double)));
+  return 0;
+}
+
+extern "C" int dwmh_s1_local_mean_align(int32_t device, const float* target, float* const* refs, int32_t k, const float* mask,
+                                        int32_t X, int32_t Y, int32_t Z, const int32_t patch_size[3], float* target_local_mu_out,
+                                        void* workspace, void* stream_) {
+  if (!target || !workspace || !patch_size || (k > 0 && !refs)) return fail("dwmh_s1_local_mean_align: null argument");
+  if (k < 0 || k > S1_MAX_REFS) return fail("dwmh_s1_local_mean_align: k = %d reference images (0..%d supported)", k, S1_MAX_REFS);
+  GridGeom q;
+  if (geom(X, Y, Z, patch_size, &q)) return 1;
+  if (q.g[2] > 300) return fail("dwmh_s1_local_mean_align: %d cells along z exceed the shared-memory tables (300)", q.g[2]);
+  if ((Y + 7) / 8 > 65535) return fail("dwmh_s1_local_mean_align: volume too large");
+  VolPtrs vols{}; vols.p[0] = const_cast<float*>(target);
+  for (int i = 0; i < k; ++i) { if (!refs[i]) return fail("dwmh_s1_local_mean_align: refs[%d] is null", i); vols.p[i + 1] = refs[i]; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  S1_CU(cudaSetDevice(device));
+  const int nvol = k + 1;
+  const size_t ncell = (size_t)q.g[0] * q.g[1] * q.g[2], gstride = align256((size_t)(q.g[0] + 2) * (q.g[1] + 2) * (q.g[2] + 2) * sizeof(double)) / sizeof(double);
+  const size_t cells_bytes = align256((size_t)nvol * ncell * 3 * sizeof(double));
+  double* cells = (double*)workspace;
+  double* mg = (double*)((char*)workspace + cells_bytes);
+  double* sg = mg + (size_t)nvol * gstride;
+  S1_CU(cudaMemsetAsync(workspace, 0, cells_bytes + 2 * (size_t)nvol * gstride * sizeof(double), st));
+  const int slabs = (q.st[0] + CS_SLAB - 1) / CS_SLAB;
+  s1_cell_sums_kernel<<<dim3((unsigned)(q.g[0] * q.g[1] * slabs), nvol), 256, 3 * q.g[2] * sizeof(double), st>>>(vols, mask, q, slabs, cells);
+  s1_grid_stats_kernel<<<dim3((unsigned)((ncell + 127) / 128), nvol), 128, 0, st>>>(cells, q, mask ? 1 : 0, mg, sg, gstride);
+  s1_zoom_align_kernel<<<dim3(X, (Y + 7) / 8, nvol), 256, 16 * (q.g[2] + 2) * sizeof(double), st>>>(mg, gstride, q, vols, target_local_mu_out);
   S1_CU(cudaGetLastError());
   return 0;
 }

@@ -70,6 +70,50 @@ def z_score(data: Array, mask: Optional[Array] = None, fill_outside: bool = Fals
     return (x, tuple(stats)) if return_stats else x
 
 
+def z_score_batch_(volumes: Sequence[torch.Tensor], mask: Optional[Array] = None, fill_outside: bool = False) -> Sequence[torch.Tensor]:
+    """z_score of up to 33 fp32 CUDA volumes sharing one mask, IN PLACE, in one pair of launches."""
+    lib = _lib.load()
+    if not volumes:
+        return volumes
+    dev = volumes[0].device
+    for v in volumes:
+        if v.device != dev or v.dtype != torch.float32 or not v.is_contiguous() or v.shape != volumes[0].shape:
+            raise ValueError("z_score_batch_: volumes must be contiguous fp32 CUDA tensors of one shape on one device")
+    m = _dev(mask, dev.index) if mask is not None else None
+    if m is not None and m.shape != volumes[0].shape:
+        raise ValueError("z_score_batch_: mask shape %s != data shape %s" % (tuple(m.shape), tuple(volumes[0].shape)))
+    ws = torch.empty(8 * len(volumes), dtype=torch.float64, device=dev)
+    ptrs = (C.c_void_p * len(volumes))(*[v.data_ptr() for v in volumes])
+    with torch.cuda.device(dev):
+        _lib.check(lib.dwmh_s1_zscore_batch(dev.index, ptrs, len(volumes), _ptr(m), volumes[0].numel(), int(bool(fill_outside)),
+                                            _ptr(ws), _stream(dev.index)))
+    return volumes
+
+
+def local_mean_align_(target: torch.Tensor, refs: Sequence[torch.Tensor], patch_size: Sequence[int], mask: Optional[Array] = None,
+                      return_local_mean: bool = True) -> Optional[torch.Tensor]:
+    """lesion_analysis.py:163-169 for a whole case in three launches: masked 50 mm local means of the target and of every
+    reference, references aligned IN PLACE (x_i - x_i_local_mu + x_prime_local_mu).  -> x_prime_local_mu (or None)."""
+    lib = _lib.load()
+    dev = target.device
+    _check3d(target, "local_mean_align_: target")
+    for v in [target] + list(refs):
+        if v.device != dev or v.dtype != torch.float32 or not v.is_contiguous() or v.shape != target.shape:
+            raise ValueError("local_mean_align_: volumes must be contiguous fp32 CUDA tensors of one shape on one device")
+    m = _dev(mask, dev.index) if mask is not None else None
+    X, Y, Z = (int(v) for v in target.shape)
+    ps = _i3(patch_size)
+    nbytes = C.c_int64(0)
+    _lib.check(lib.dwmh_s1_local_mean_align_workspace(X, Y, Z, ps, len(refs), C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    mu = torch.empty_like(target) if return_local_mean else None
+    ptrs = (C.c_void_p * max(1, len(refs)))(*[r.data_ptr() for r in refs])
+    with torch.cuda.device(dev):
+        _lib.check(lib.dwmh_s1_local_mean_align(dev.index, _ptr(target), ptrs, len(refs), _ptr(m), X, Y, Z, ps, _ptr(mu), _ptr(ws),
+                                                _stream(dev.index)))
+    return mu
+
+
 def mean_std_grid(data: Array, patch_size: Sequence[int], order: int = 1, mask: Optional[Array] = None,
                   device: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """image_ops.py:56-170 (order 1, the value every call site in the reference uses)."""
@@ -199,13 +243,12 @@ def nll_anomaly_map(x_prime: Array, x_refs: Sequence[Array], m_rough_brain: Arra
     patch = list(image_patch) if image_patch is not None else image_patch_size(physical_voxel_size)
     brain = _dev(m_rough_brain, device)
     valid = _dev(m_valid_score, device)
-    xp = z_score(x_prime, brain, fill_outside=True, device=device)
-    refs = [z_score(r, brain, fill_outside=True, device=device) for r in x_refs]
-    mu_p, _ = mean_std_grid(xp, patch, mask=valid, device=device)
-    if mean_correction:
-        for r in refs:
-            mu_i, _ = mean_std_grid(r, patch, mask=valid, device=device)
-            align_local_mean_(r, mu_i, mu_p)
+    # one device copy per volume, then the whole case per launch: z-score + tissue-min fill of the k + 1 volumes (2 launches),
+    # local means + alignment (3 launches), NLL (1 launch)
+    xp = _dev(x_prime, device, copy=True)
+    refs = [_dev(r, device, copy=True) for r in x_refs]
+    z_score_batch_([xp] + refs, brain, fill_outside=True)
+    mu_p = local_mean_align_(xp, refs if mean_correction else [], patch, mask=valid)
     an, mean, std = nll(xp, refs, min_std=min_std, side=intensity_prior, return_all=True, mul_mask=valid, device=device)
     out = {"normalized_input": xp, "local_mean": mu_p * valid, "anomaly": an, "mean": mean, "std": std}
     if with_reference_scores:

@@ -124,12 +124,24 @@ int dwmh_remove_sparks(dwmh_ctx* ctx, const uint8_t* seg_dev, int32_t X, int32_t
  *   workspace: >= 64 bytes of device memory.  stats_out (host, may be NULL) = {mean, std, count} (synchronises). */
 int dwmh_s1_zscore(int32_t device, float* x_dev, const float* mask_dev, int64_t n, int32_t fill_outside, void* workspace_dev,
                    double* stats_out, void* stream);
+/* The same for nvol <= 33 volumes sharing one mask in ONE launch pair (target + registered references of a case):
+ * xs = HOST array of nvol device pointers; workspace >= 64 * nvol bytes. */
+int dwmh_s1_zscore_batch(int32_t device, float* const* xs, int32_t nvol, const float* mask_dev, int64_t n, int32_t fill_outside,
+                         void* workspace_dev, void* stream);
 /* mean_std_grid(data, patch_size, order=1, mask) (image_ops.py:56-170): mean / std of the half-overlapping patch blocks
  * of the zero-padded volume, zero-bordered, linearly zoomed by the step (scipy.ndimage.zoom, order 1) and cropped.
  * mask_dev NULL = the unmasked branch; std_out_dev may be NULL.  workspace: dwmh_s1_mean_std_grid_workspace() bytes. */
 int dwmh_s1_mean_std_grid_workspace(int32_t X, int32_t Y, int32_t Z, const int32_t patch_size[3], int64_t* bytes);
 int dwmh_s1_mean_std_grid(int32_t device, const float* x_dev, const float* mask_dev, int32_t X, int32_t Y, int32_t Z,
                           const int32_t patch_size[3], float* mean_out_dev, float* std_out_dev, void* workspace_dev, void* stream);
+/* lesion_analysis.py:163-169 fused for a whole case: local mean of the target and of the k references (k <= 32, may be 0;
+ * refs = HOST array of device pointers), then every reference aligned in place, x_i = x_i - x_i_local_mu + x_prime_local_mu,
+ * evaluated from the coarse grids (the references' local-mean volumes are never written).  target_local_mu_out_dev
+ * (may be NULL) receives x_prime_local_mu.  Three launches in total. */
+int dwmh_s1_local_mean_align_workspace(int32_t X, int32_t Y, int32_t Z, const int32_t patch_size[3], int32_t k, int64_t* bytes);
+int dwmh_s1_local_mean_align(int32_t device, const float* target_dev, float* const* refs, int32_t k, const float* mask_dev,
+                             int32_t X, int32_t Y, int32_t Z, const int32_t patch_size[3], float* target_local_mu_out_dev,
+                             void* workspace_dev, void* stream);
 /* x = x - local_mu + target_local_mu, in place (lesion_analysis.py:166-169: align a reference to the target). */
 int dwmh_s1_align_local_mean(int32_t device, float* x_dev, const float* local_mu_dev, const float* target_local_mu_dev, int64_t n, void* stream);
 /* nll(x_prime, x_refs, min_std, side, return_all) (lesion_analysis.py:84-113, use_mask=False) with group_mean / group_std

@@ -113,6 +113,35 @@ def test_anomaly_pipeline_matches_reference_fixture(g, S):
     assert np.unravel_index(np.argmax(h(r["anomaly"])), g["in_target"].shape)[0] in range(12, 16)
 
 
+def test_batched_case_launches_equal_the_function_by_function_path(g, S):
+    """dwmh_s1_zscore_batch / dwmh_s1_local_mean_align (whole case per launch) against z_score / mean_std_grid /
+    align_local_mean_ called volume by volume."""
+    brain, valid, patch = g["in_brain"], g["in_valid"], [14, 14, 14]
+    vols = [torch.from_numpy(v.copy()).cuda() for v in [g["in_target"]] + list(g["in_refs"])]
+    S.z_score_batch_(vols, brain, fill_outside=True)
+    single = [S.z_score(v, brain, fill_outside=True) for v in [g["in_target"]] + list(g["in_refs"])]
+    for a, b in zip(vols, single):
+        assert np.allclose(h(a), h(b), rtol=0, atol=1e-6)               # fp64 atomics: summation order is free
+    z0 = h(vols[0]).copy()
+    mu_p = S.local_mean_align_(vols[0], vols[1:], patch, mask=valid)
+    mu_ref, _ = S.mean_std_grid(single[0], patch, mask=valid)
+    assert np.allclose(h(mu_p), h(mu_ref), rtol=0, atol=1e-6)          # fp64 atomics: summation order is free
+    for a, b in zip(vols[1:], single[1:]):
+        mu_i, _ = S.mean_std_grid(b, patch, mask=valid)
+        S.align_local_mean_(b, mu_i, mu_ref)
+        assert np.allclose(h(a), h(b), rtol=0, atol=2e-6)               # fused path skips the fp32 rounding of the two means
+    assert np.array_equal(h(vols[0]), z0)                              # the target is read only
+    # k = 0: local mean only; unmasked statistics; unaligned (odd-offset) views take the scalar kernels
+    assert np.allclose(h(S.local_mean_align_(single[0], [], patch, mask=valid)), h(mu_ref), atol=1e-6)
+    flat = torch.zeros(g["in_target"].size + 1, device="cuda")
+    odd = flat[1:].view(g["in_target"].shape)
+    odd.copy_(torch.from_numpy(g["in_target"]))
+    S.z_score_batch_([odd], brain, fill_outside=True)
+    assert np.allclose(h(odd), h(single[0]), rtol=0, atol=1e-6)
+    with pytest.raises(ValueError):
+        S.z_score_batch_([vols[0], vols[1][:-1]], brain)
+
+
 def test_full_size_volume_against_oracle(S):
     """BASELINE.json's 182x218x182 shape, 1 mm isotropic: 50-voxel local-mean patch, 3x3x3 median."""
     import oracle as O
