@@ -28,14 +28,14 @@ __device__ __forceinline__ void ccl_union(int* L, int a, int b) {
 }
 
 // mask: voxel > 0 (uint8 label map) ; labels[v] = v for foreground, -1 for background
-__global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ seg, int* __restrict__ L, int* __restrict__ size, int64_t V) {
+static __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ seg, int* __restrict__ L, int* __restrict__ size, int64_t V) {
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
     L[v] = seg[v] ? (int)v : -1;
     size[v] = 0;
   }
 }
 
-__global__ void __launch_bounds__(256) ccl_merge_kernel(int* __restrict__ L, int X, int Y, int Z) {
+static __global__ void __launch_bounds__(256) ccl_merge_kernel(int* __restrict__ L, int X, int Y, int Z) {
   const int64_t V = (int64_t)X * Y * Z;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
     if (L[v] < 0) continue;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(int* __restrict__ L, int
   }
 }
 
-__global__ void __launch_bounds__(256) ccl_count_kernel(int* __restrict__ L, int* __restrict__ size, int64_t V) {
+static __global__ void __launch_bounds__(256) ccl_count_kernel(int* __restrict__ L, int* __restrict__ size, int64_t V) {
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
     if (L[v] < 0) continue;
     const int r = ccl_find(L, (int)v);
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) ccl_count_kernel(int* __restrict__ L, int
   }
 }
 
-__global__ void __launch_bounds__(256) ccl_filter_kernel(const int* __restrict__ L, const int* __restrict__ size, uint8_t* __restrict__ out,
+static __global__ void __launch_bounds__(256) ccl_filter_kernel(const int* __restrict__ L, const int* __restrict__ size, uint8_t* __restrict__ out,
                                                          int min_volume, int64_t V) {
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
     const int r = L[v];

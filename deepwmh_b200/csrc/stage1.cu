@@ -7,6 +7,7 @@
 //   dwmh_s1_align_local_mean  x_i - x_i_local_mu + x_prime_local_mu (lesion_analysis.py:166-169)
 //   dwmh_s1_group_nll         group_mean / group_std / nll (image_ops.py:197-231, lesion_analysis.py:84-113)
 //   dwmh_s1_median_filter     median_filter(mode='constant', cval=0) behind median_3mm (image_ops.py:181-183,378-421)
+//   dwmh_s1_component_filtering  component_filtering (image_ops.py:253-306)
 #include "../../include/deepwmh_b200.h"
 
 #include <cstdarg>
@@ -15,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "common.cuh"
+#include "kernels_ccl.cuh"
 
 extern "C" void dwmh_internal_set_error(const char* msg);   // api.cu (thread-local message behind dwmh_last_error)
 
@@ -435,6 +437,74 @@ __global__ void __launch_bounds__(256) s1_median_small_kernel(const float* __res
   out[((int64_t)gx * Y + gy) * Z + gz] = key2f(v[1]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// component_filtering (image_ops.py:253-306).  Per filtered orientation `ax`: 2-D binary erosion of every slice
+// (scipy's cross, border = background) fused into the label initialisation, union-find over the two in-plane axes
+// (roots = smallest voxel index = scipy's raster label order), component sizes, per-slice winner by a packed 64-bit
+// atomicMax {size, ~root} (largest component, first label on ties), membership added to the running sum `acc`.
+// Orientations that are not filtered add the mask itself; the result is acc > 0.5.
+// ---------------------------------------------------------------------------------------------------------------
+struct Dims { int n[3]; int64_t stride[3]; };
+__device__ __forceinline__ void cf_coords(int64_t v, const Dims& d, int (&c)[3]) {
+  c[2] = (int)(v % d.n[2]); c[1] = (int)((v / d.n[2]) % d.n[1]); c[0] = (int)(v / ((int64_t)d.n[2] * d.n[1]));
+}
+
+__global__ void __launch_bounds__(256) cf_erode_init_kernel(const float* __restrict__ mask, int* __restrict__ L, int* __restrict__ size,
+                                                            Dims d, int ax, int64_t V) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+    int c[3];
+    cf_coords(v, d, c);
+    bool keep = mask[v] != 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      if (a != ax && keep)
+        keep = c[a] > 0 && c[a] + 1 < d.n[a] && mask[v - d.stride[a]] != 0.f && mask[v + d.stride[a]] != 0.f;
+    L[v] = keep ? (int)v : -1;
+    size[v] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) cf_merge_kernel(int* __restrict__ L, Dims d, int ax, int64_t V) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+    if (L[v] < 0) continue;
+    int c[3];
+    cf_coords(v, d, c);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      if (a != ax && c[a] + 1 < d.n[a] && L[v + d.stride[a]] >= 0) dwmh::ccl_union(L, (int)v, (int)(v + d.stride[a]));
+  }
+}
+
+__global__ void __launch_bounds__(256) cf_best_kernel(const int* __restrict__ L, const int* __restrict__ size,
+                                                      unsigned long long* __restrict__ best, Dims d, int ax, int64_t V) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+    if (L[v] != (int)v) continue;                                    // component roots only
+    int c[3];
+    cf_coords(v, d, c);
+    atomicMax(best + c[ax], ((unsigned long long)(unsigned)size[v] << 32) | (unsigned long long)(0xffffffffu - (unsigned)v));
+  }
+}
+
+__global__ void __launch_bounds__(256) cf_accum_kernel(const int* __restrict__ L, const unsigned long long* __restrict__ best,
+                                                       float* __restrict__ acc, Dims d, int ax, int64_t V) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+    const int r = L[v];
+    if (r < 0) continue;
+    int c[3];
+    cf_coords(v, d, c);
+    const unsigned long long b = best[c[ax]];
+    if (b != 0ull && (unsigned)r == 0xffffffffu - (unsigned)(b & 0xffffffffull)) acc[v] += 1.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) cf_passthrough_kernel(const float* __restrict__ mask, float* __restrict__ acc, int64_t V) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) acc[v] += mask[v];
+}
+
+__global__ void __launch_bounds__(256) cf_final_kernel(const float* __restrict__ acc, float* __restrict__ out, int64_t V) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) out[v] = acc[v] > 0.5f ? 1.f : 0.f;
+}
+
 int geom(int X, int Y, int Z, const int32_t patch[3], GridGeom* q) {
   if (X <= 0 || Y <= 0 || Z <= 0) return fail("mean_std_grid: empty volume");
   q->X = X; q->Y = Y; q->Z = Z;
@@ -616,6 +686,51 @@ extern "C" int dwmh_s1_median_filter(int32_t device, const float* in, float* out
   else if (kx == 3 && ky == 1 && kz == 3) s1_median_small_kernel<3, 1, 3><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
   else if (kx == 3 && ky == 3 && kz == 1) s1_median_small_kernel<3, 3, 1><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
   else s1_median_kernel<<<grid, 256, smem, st>>>(in, out, X, Y, Z, kx, ky, kz);
+  S1_CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwmh_s1_component_filtering_workspace(int32_t X, int32_t Y, int32_t Z, int64_t* bytes) {
+  if (!bytes) return fail("dwmh_s1_component_filtering_workspace: null argument");
+  if (X <= 0 || Y <= 0 || Z <= 0) return fail("dwmh_s1_component_filtering_workspace: empty volume");
+  const size_t V = (size_t)X * Y * Z, m = (size_t)(X > Y ? (X > Z ? X : Z) : (Y > Z ? Y : Z));
+  *bytes = (int64_t)(3 * align256(V * 4) + align256(m * 8));
+  return 0;
+}
+
+extern "C" int dwmh_s1_component_filtering(int32_t device, const float* mask, int32_t X, int32_t Y, int32_t Z, const double voxel_size[3],
+                                           float* out, void* workspace, void* stream_) {
+  if (!mask || !out || !workspace || !voxel_size) return fail("dwmh_s1_component_filtering: null argument");
+  if (X <= 0 || Y <= 0 || Z <= 0) return fail("dwmh_s1_component_filtering: empty volume");
+  const int64_t V = (int64_t)X * Y * Z;
+  if (V >= (int64_t)1 << 31) return fail("dwmh_s1_component_filtering: volume of %lld voxels exceeds the 32-bit label range", (long long)V);
+  for (int a = 0; a < 3; ++a) if (!(voxel_size[a] > 0.0)) return fail("dwmh_s1_component_filtering: voxel_size[%d] must be positive", a);
+  // thick-slice data (max / min > 3): only the slices across the thick axis are filtered (np.argmax: first maximum)
+  const double mx = fmax(voxel_size[0], fmax(voxel_size[1], voxel_size[2])), mn = fmin(voxel_size[0], fmin(voxel_size[1], voxel_size[2]));
+  bool filt[3] = {true, true, true};
+  if (mx / mn > 3.0) {
+    const int am = voxel_size[0] >= voxel_size[1] ? (voxel_size[0] >= voxel_size[2] ? 0 : 2) : (voxel_size[1] >= voxel_size[2] ? 1 : 2);
+    for (int a = 0; a < 3; ++a) filt[a] = a == am;
+  }
+  cudaStream_t st = (cudaStream_t)stream_;
+  S1_CU(cudaSetDevice(device));
+  int* L = (int*)workspace;
+  int* size = (int*)((char*)workspace + align256((size_t)V * 4));
+  float* acc = (float*)((char*)workspace + 2 * align256((size_t)V * 4));
+  unsigned long long* best = (unsigned long long*)((char*)workspace + 3 * align256((size_t)V * 4));
+  const Dims d{{X, Y, Z}, {(int64_t)Y * Z, (int64_t)Z, 1}};
+  const int grid = grid_for(device);
+  S1_CU(cudaMemsetAsync(acc, 0, (size_t)V * 4, st));
+  for (int ax = 0; ax < 3; ++ax) {
+    if (!filt[ax]) { cf_passthrough_kernel<<<grid, 256, 0, st>>>(mask, acc, V); continue; }
+    S1_CU(cudaMemsetAsync(best, 0, (size_t)d.n[ax] * 8, st));
+    cf_erode_init_kernel<<<grid, 256, 0, st>>>(mask, L, size, d, ax, V);
+    cf_merge_kernel<<<grid, 256, 0, st>>>(L, d, ax, V);
+    dwmh::ccl_count_kernel<<<grid, 256, 0, st>>>(L, size, V);
+    cf_best_kernel<<<grid, 256, 0, st>>>(L, size, best, d, ax, V);
+    cf_accum_kernel<<<grid, 256, 0, st>>>(L, best, acc, d, ax, V);
+  }
+  cf_final_kernel<<<grid, 256, 0, st>>>(acc, out, V);
   S1_CU(cudaGetLastError());
   return 0;
 }

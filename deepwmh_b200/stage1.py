@@ -3,14 +3,15 @@
 Host-side mirror of the array functions the reference uses in `nll_analysis`
 (deepwmh/analysis/lesion_analysis.py:115-181): same names, argument meaning and defaults as
 
-    z_score, mean_std_grid, median_filter, median_3mm, group_mean, group_std   deepwmh/analysis/image_ops.py
+    z_score, mean_std_grid, median_filter, median_3mm, group_mean, group_std,
+    component_filtering                                                        deepwmh/analysis/image_ops.py
     nll                                                                        deepwmh/analysis/lesion_analysis.py:84-113
 
 over the `dwmh_s1_*` entry points of include/deepwmh_b200.h.  Inputs may be numpy arrays or CUDA tensors [X, Y, Z];
 results are fp32 CUDA tensors.  There is no CPU path: every function needs the library and a GPU.
 
-Not built: the Otsu branches (`apply_otsu`, `nll(use_mask=True)` -- skimage), `component_filtering` (2-D per-slice
-erosion + largest component: host-side mask preparation), the histogram / threshold search and the NIfTI / plot output.
+Not built: the Otsu branches (`apply_otsu`, `nll(use_mask=True)` -- skimage), the histogram / threshold search and the
+NIfTI / plot output.
 """
 from __future__ import annotations
 
@@ -225,6 +226,28 @@ def median_3mm(data: Array, physical_voxel_size: Sequence[float], device: int = 
     return median_filter(data, median_kernel_size(physical_voxel_size), device=device)
 
 
+def component_filtering(mask: Array, voxel_size: Sequence[float], return_type: str = "float32", erosion: bool = True,
+                        device: int = 0) -> torch.Tensor:
+    """image_ops.py:253-306 ("quickly refines the calculated brain mask"); `erosion` is accepted and, as in the reference,
+    ignored (the slices are always eroded)."""
+    if return_type != "float32":
+        raise NotImplementedError("component_filtering: only return_type='float32' is built")
+    lib = _lib.load()
+    m = _dev(mask, device)
+    _check3d(m, "component_filtering: mask")
+    X, Y, Z = (int(v) for v in m.shape)
+    if len(voxel_size) != 3:
+        raise ValueError("component_filtering: voxel_size needs three values")
+    vs = (C.c_double * 3)(*[float(v) for v in voxel_size])
+    nbytes = C.c_int64(0)
+    _lib.check(lib.dwmh_s1_component_filtering_workspace(X, Y, Z, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=m.device)
+    out = torch.empty_like(m)
+    with torch.cuda.device(m.device):
+        _lib.check(lib.dwmh_s1_component_filtering(device, _ptr(m), X, Y, Z, vs, _ptr(out), _ptr(ws), _stream(device)))
+    return out
+
+
 def image_patch_size(physical_voxel_size: Sequence[float], physical_patch_size=(50, 50, 50)) -> List[int]:
     """lesion_analysis.py:124-131: the 50 mm local-mean patch in voxels."""
     return [int(np.ceil(p / v)) for p, v in zip(physical_patch_size, physical_voxel_size)]
@@ -233,7 +256,7 @@ def image_patch_size(physical_voxel_size: Sequence[float], physical_patch_size=(
 def nll_anomaly_map(x_prime: Array, x_refs: Sequence[Array], m_rough_brain: Array, m_valid_score: Array,
                     physical_voxel_size: Sequence[float] = (1.0, 1.0, 1.0), intensity_prior: Optional[str] = None,
                     mean_correction: bool = True, min_std: float = 0.03, image_patch: Optional[Sequence[int]] = None,
-                    with_reference_scores: bool = False, device: int = 0) -> dict:
+                    with_reference_scores: bool = False, apply_component_filtering: bool = False, device: int = 0) -> dict:
     """The array part of `nll_analysis` (lesion_analysis.py:142-186) from raw registered volumes and the two masks:
     z-score over the rough brain mask + tissue-min fill (target and every reference), 50 mm local-mean alignment of the
     references to the target, voxelwise Gaussian NLL with sigma floored at `min_std`, masked by the valid-score mask.
@@ -250,6 +273,8 @@ def nll_anomaly_map(x_prime: Array, x_refs: Sequence[Array], m_rough_brain: Arra
     z_score_batch_([xp] + refs, brain, fill_outside=True)
     mu_p = local_mean_align_(xp, refs if mean_correction else [], patch, mask=valid)
     an, mean, std = nll(xp, refs, min_std=min_std, side=intensity_prior, return_all=True, mul_mask=valid, device=device)
+    if apply_component_filtering:                                    # lesion_analysis.py:176 (the target's score only)
+        an = an * component_filtering(valid, physical_voxel_size, device=device)
     out = {"normalized_input": xp, "local_mean": mu_p * valid, "anomaly": an, "mean": mean, "std": std}
     if with_reference_scores:
         out["reference_anomalies"] = [nll(r, refs, min_std=min_std, side=intensity_prior, mul_mask=valid, device=device) for r in refs]

@@ -155,6 +155,14 @@ int dwmh_s1_group_nll(int32_t device, const float* x_prime_dev, const float* con
 int dwmh_s1_median_filter(int32_t device, const float* in_dev, float* out_dev, int32_t X, int32_t Y, int32_t Z,
                           const int32_t kernel_size[3], void* stream);
 
+/* component_filtering(mask, voxel_size) (image_ops.py:253-306): per slice of every filtered orientation, 2-D erosion and the
+ * largest 4-connected component (first label on ties); thin-slice data filters all three orientations, thick-slice data
+ * (max / min voxel size > 3) only across the thick axis while the other two orientations add the mask itself; out = sum > 0.5
+ * as 0 / 1 floats.  Integer work, bit-exact.  workspace: dwmh_s1_component_filtering_workspace() bytes; mask != out. */
+int dwmh_s1_component_filtering_workspace(int32_t X, int32_t Y, int32_t Z, int64_t* bytes);
+int dwmh_s1_component_filtering(int32_t device, const float* mask_dev, int32_t X, int32_t Y, int32_t Z, const double voxel_size[3],
+                                float* out_dev, void* workspace_dev, void* stream);
+
 /* --- a6 end to end with HOST buffers (what predict_preprocessed_data_return_seg_and_softmax does):
  * raw fp32 volume [X][Y][Z] in host memory -> (optional z-score, mask_mode as above, <0 = skip)
  * -> tiled prediction -> host softmax fp32 [2][X][Y][Z] and seg uint8 [X][Y][Z].  H2D/D2H inside. */

@@ -14,7 +14,7 @@ from __future__ import annotations
 from typing import List, Optional, Sequence
 
 import numpy as np
-from scipy.ndimage import label, median_filter, zoom
+from scipy.ndimage import binary_erosion, label, median_filter, zoom
 
 SQRT_2PI_REF = 2.506   # the reference's rounded sqrt(2 pi), deepwmh/analysis/lesion_analysis.py:103
 
@@ -161,6 +161,31 @@ def median_kernel(voxel_size: Sequence[float]) -> List[int]:
 
 def median_3mm(data, voxel_size):
     return median_filter(np.asarray(data), size=median_kernel(voxel_size), mode="constant", cval=0)
+
+
+def component_filtering(mask, voxel_size):
+    """component_filtering, image_ops.py:253-306: for every slice of every filtered orientation keep the largest
+    4-connected component of the eroded slice (ties: the first label in raster order); thin-slice data (max / min voxel
+    size <= 3) filters all three orientations, thick-slice data only the slices across the thick axis while the other two
+    orientations contribute the mask itself; result = (sum of the three volumes) > 0.5."""
+    mask = np.asarray(mask)
+    vs = [float(v) for v in voxel_size]
+    axes = [int(np.argmax(vs))] if max(vs) / min(vs) > 3 else [0, 1, 2]
+    total = np.zeros(mask.shape, np.float32)
+    for ax in range(3):
+        if ax not in axes:
+            total += mask.astype(np.float32)
+            continue
+        vol = np.zeros(mask.shape, np.float32)
+        for s_ in range(mask.shape[ax]):
+            sl = [slice(None)] * 3
+            sl[ax] = s_
+            lab, n = label(binary_erosion(mask[tuple(sl)]))
+            if n:
+                sizes = np.bincount(lab.ravel(), minlength=n + 1)[1:]
+                vol[tuple(sl)] = lab == 1 + int(np.argmax(sizes))      # argmax: first of equal maxima
+        total += vol
+    return (total > 0.5).astype(np.float32)
 
 
 def nll_anomaly_arrays(target, refs, brain, valid, patch, min_std=0.03, side="+", mean_correction=True):

@@ -3,7 +3,7 @@
 
 The arithmetic either side of the network -- z_score, remove_sparks / remove_3mm_sparks, the stage-2 softmax masking
 and checkpoint ensembling, the stage-1 NLL anomaly map pieces (group_mean / group_std / nll / mean_std_grid /
-median_3mm) and the Dice of analysis/metrics.py -- lives in /root/reference itself, so unlike the un-vendored nnU-Net
+median_3mm / component_filtering) and the Dice of analysis/metrics.py -- lives in /root/reference itself, so unlike the un-vendored nnU-Net
 engine these rows CAN be pinned: this script imports
 
     deepwmh/analysis/image_ops.py, deepwmh/analysis/lesion_analysis.py, deepwmh/pipeline/DCNN_multistage.py
@@ -159,6 +159,18 @@ def main():
     out["pipe_x_prime"], out["pipe_local_mu"] = x_prime, mu_p
     out["pipe_anomaly"], out["pipe_mean"], out["pipe_std"] = an * valid, xm, xs_
     out["pipe_ref_anomaly0"] = la.nll(x_i[0], x_i, min_std=0.03, side="+") * valid
+
+    # ---- component_filtering (image_ops.py:253-306): per-slice erosion + largest component, three orientations
+    speck = valid.copy()
+    speck[2:4, 3:6, 4:6] = 1.0                                      # sparks outside the brain, to be filtered away
+    speck[36:39, 40:43, 30:34] = 1.0
+    out["cf_in"] = speck
+    for vox, tag in (([1.0, 1.0, 1.0], "iso"), ([0.9, 0.9, 4.0], "thick_z"), ([5.0, 1.0, 1.0], "thick_x")):
+        out["cf_" + tag] = io.component_filtering(speck, vox).astype(np.float32)
+        out["cf_vox_" + tag] = np.array(vox)
+    out["cf_brain"] = io.component_filtering(brain, [1.0, 1.0, 1.0]).astype(np.float32)
+    out["cf_empty"] = io.component_filtering(np.zeros((6, 7, 5), "float32"), [1.0, 1.0, 1.0]).astype(np.float32)
+    out["pipe_anomaly_cf"] = an * valid * io.component_filtering(valid, [1.0, 1.0, 1.0])      # lesion_analysis.py:175-176
 
     conv = {}
     for k_, v in out.items():

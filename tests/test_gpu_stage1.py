@@ -113,6 +113,27 @@ def test_anomaly_pipeline_matches_reference_fixture(g, S):
     assert np.unravel_index(np.argmax(h(r["anomaly"])), g["in_target"].shape)[0] in range(12, 16)
 
 
+@pytest.mark.parametrize("tag", ["iso", "thick_z", "thick_x"])
+def test_component_filtering_bit_exact_with_reference_fixture(g, S, tag):
+    got = h(S.component_filtering(g["cf_in"], g["cf_vox_" + tag].tolist()))
+    assert got.dtype == np.float32 and np.array_equal(got, g["cf_" + tag])
+
+
+def test_component_filtering_edge_cases(g, S):
+    assert np.array_equal(h(S.component_filtering(g["in_brain"], [1.0, 1.0, 1.0])), g["cf_brain"])
+    assert h(S.component_filtering(np.zeros((6, 7, 5), np.float32), [1.0, 1.0, 1.0])).sum() == 0
+    rng = np.random.default_rng(21)
+    for shape, thr, vox in (((9, 31, 17), 0.35, [1.0, 1.0, 1.0]), ((40, 40, 40), 0.2, [1.0, 2.0, 1.5]), ((12, 50, 33), 0.3, [1.0, 3.5, 1.0]),
+                            ((1, 20, 20), 0.2, [1.0, 1.0, 1.0]), ((64, 64, 48), 0.12, [0.8, 0.8, 0.8])):
+        m = (rng.random(shape) > thr).astype(np.float32)              # many equal-size components: exercises the tie rule
+        assert np.array_equal(h(S.component_filtering(m, vox)), I.component_filtering(m, vox)), (shape, vox)
+    r = S.nll_anomaly_map(g["in_target"], list(g["in_refs"]), g["in_brain"], g["in_valid"], intensity_prior="+",
+                          image_patch=g["pipe_patch"].tolist(), apply_component_filtering=True)
+    assert np.allclose(h(r["anomaly"]), g["pipe_anomaly_cf"], rtol=1e-4, atol=2e-3)
+    with pytest.raises(NotImplementedError):
+        S.component_filtering(g["in_brain"], [1.0, 1.0, 1.0], return_type="int")
+
+
 def test_batched_case_launches_equal_the_function_by_function_path(g, S):
     """dwmh_s1_zscore_batch / dwmh_s1_local_mean_align (whole case per launch) against z_score / mean_std_grid /
     align_local_mean_ called volume by volume."""

@@ -87,6 +87,18 @@ def test_median_3mm(g, tag, ks):
     assert np.array_equal(I.median_3mm(g["nll_pos"], vox), g["median_" + tag])
 
 
+@pytest.mark.parametrize("tag", ["iso", "thick_z", "thick_x"])
+def test_component_filtering(g, tag):
+    assert np.array_equal(I.component_filtering(g["cf_in"], g["cf_vox_" + tag].tolist()), g["cf_" + tag])
+
+
+def test_component_filtering_edge_cases(g):
+    assert np.array_equal(I.component_filtering(g["in_brain"], [1.0, 1.0, 1.0]), g["cf_brain"])
+    assert np.array_equal(I.component_filtering(np.zeros((6, 7, 5), np.float32), [1.0, 1.0, 1.0]), g["cf_empty"])
+    assert g["cf_iso"].sum() < g["cf_in"].sum() and g["cf_iso"][2:4, 3:6, 4:6].sum() == 0      # the sparks are gone
+    assert np.array_equal(g["cf_thick_z"], g["cf_in"])             # thick slices: two orientations pass the mask through
+
+
 def test_anomaly_pipeline(g):
     r = I.nll_anomaly_arrays(g["in_target"], list(g["in_refs"]), g["in_brain"], g["in_valid"], g["pipe_patch"].tolist())
     assert np.allclose(r["x_prime"], g["pipe_x_prime"], rtol=1e-5, atol=1e-5)
