@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #include "common.cuh"
@@ -505,6 +506,55 @@ __global__ void __launch_bounds__(256) cf_final_kernel(const float* __restrict__
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) out[v] = acc[v] > 0.5f ? 1.f : 0.f;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Otsu threshold support (skimage.filters.threshold_otsu as called at lesion_analysis.py:145-146 and image_ops.py:308-323):
+// min / max over a mask, and numpy.histogram's equal-width binning with its exact edge corrections (bin i holds
+// edges[i] <= v < edges[i+1], the last bin is closed); the 256-entry Otsu scan itself runs on the host.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) s1_minmax_kernel(const float* __restrict__ x, const float* __restrict__ mask, int64_t n,
+                                                        int* __restrict__ mm) {       // mm[0] = min, mm[1] = max (ordered ints)
+  int mn = 0x7fffffff, mx = (int)0x80000000;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (!mask || mask[i] > 0.5f) { const int o = f2ord(x[i]); mn = min(mn, o); mx = max(mx, o); }
+  mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm, mn); atomicMax(mm + 1, mx); }
+}
+
+// voxels outside the mask count as `fill` (np.where(mask < 0.5, fill, x)) when fill_outside, else they are skipped
+__global__ void __launch_bounds__(256) s1_histogram_kernel(const float* __restrict__ x, const float* __restrict__ mask, int64_t n,
+                                                           int fill_outside, float fill, const double* __restrict__ edges, int nbins,
+                                                           unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned char hsm[];
+  double* e = reinterpret_cast<double*>(hsm);                         // [nbins + 1]
+  unsigned int* h = reinterpret_cast<unsigned int*>(e + nbins + 1);   // [nbins]
+  for (int i = threadIdx.x; i <= nbins; i += blockDim.x) e[i] = edges[i];
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) h[i] = 0u;
+  __syncthreads();
+  const double first = e[0], last = e[nbins], norm = (double)nbins / (last - first);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = x[i];
+    if (mask && !(mask[i] >= 0.5f)) { if (!fill_outside) continue; v = fill; }
+    const double d = (double)v;
+    if (!(d >= first && d <= last)) continue;                         // outside the range (and NaN): not counted
+    int b = (int)((d - first) * norm);
+    b = b < 0 ? 0 : (b > nbins - 1 ? nbins - 1 : b);
+    if (d < e[b]) --b;
+    else if (b != nbins - 1 && d >= e[b + 1]) ++b;
+    atomicAdd(&h[b], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) if (h[i]) atomicAdd(counts + i, (unsigned long long)h[i]);
+}
+
+__global__ void __launch_bounds__(256) s1_threshold_kernel(const float* __restrict__ x, float thr, const float* __restrict__ mul,
+                                                           float* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = (x[i] > thr ? 1.f : 0.f) * (mul ? mul[i] : 1.f);
+}
+
 int geom(int X, int Y, int Z, const int32_t patch[3], GridGeom* q) {
   if (X <= 0 || Y <= 0 || Z <= 0) return fail("mean_std_grid: empty volume");
   q->X = X; q->Y = Y; q->Z = Z;
@@ -731,6 +781,47 @@ extern "C" int dwmh_s1_component_filtering(int32_t device, const float* mask, in
     cf_accum_kernel<<<grid, 256, 0, st>>>(L, best, acc, d, ax, V);
   }
   cf_final_kernel<<<grid, 256, 0, st>>>(acc, out, V);
+  S1_CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwmh_s1_minmax(int32_t device, const float* x, const float* mask, int64_t n, void* workspace, float out_minmax[2], void* stream_) {
+  if (!x || !workspace || !out_minmax) return fail("dwmh_s1_minmax: null argument");
+  if (n <= 0) return fail("dwmh_s1_minmax: empty volume");
+  cudaStream_t st = (cudaStream_t)stream_;
+  S1_CU(cudaSetDevice(device));
+  const int init[2] = {0x7fffffff, (int)0x80000000};
+  int* mm = (int*)workspace;
+  S1_CU(cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, st));
+  s1_minmax_kernel<<<grid_for(device), 256, 0, st>>>(x, mask, n, mm);
+  S1_CU(cudaGetLastError());
+  int h[2];
+  S1_CU(cudaMemcpyAsync(h, mm, sizeof h, cudaMemcpyDeviceToHost, st));
+  S1_CU(cudaStreamSynchronize(st));
+  if (h[0] == 0x7fffffff) return fail("dwmh_s1_minmax: the mask selects no voxel");
+  for (int i = 0; i < 2; ++i) { const int o = h[i] >= 0 ? h[i] : h[i] ^ 0x7fffffff; memcpy(&out_minmax[i], &o, 4); }
+  return 0;
+}
+
+extern "C" int dwmh_s1_histogram(int32_t device, const float* x, const float* mask, int64_t n, int32_t fill_outside, float fill_value,
+                                 const double* edges, int32_t nbins, uint64_t* counts, void* stream_) {
+  if (!x || !edges || !counts) return fail("dwmh_s1_histogram: null argument");
+  if (n <= 0) return fail("dwmh_s1_histogram: empty volume");
+  if (nbins < 1 || nbins > 2048) return fail("dwmh_s1_histogram: nbins = %d (1..2048 supported)", nbins);
+  cudaStream_t st = (cudaStream_t)stream_;
+  S1_CU(cudaSetDevice(device));
+  S1_CU(cudaMemsetAsync(counts, 0, (size_t)nbins * sizeof(uint64_t), st));
+  const size_t smem = (size_t)(nbins + 1) * sizeof(double) + (size_t)nbins * sizeof(unsigned int);
+  s1_histogram_kernel<<<grid_for(device) / 2, 256, smem, st>>>(x, mask, n, fill_outside, fill_value, edges, nbins,
+                                                                 reinterpret_cast<unsigned long long*>(counts));
+  S1_CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwmh_s1_threshold_mask(int32_t device, const float* x, float threshold, const float* mul_mask, float* out, int64_t n, void* stream_) {
+  if (!x || !out) return fail("dwmh_s1_threshold_mask: null argument");
+  S1_CU(cudaSetDevice(device));
+  s1_threshold_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x, threshold, mul_mask, out, n);
   S1_CU(cudaGetLastError());
   return 0;
 }

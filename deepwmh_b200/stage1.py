@@ -10,8 +10,8 @@ Host-side mirror of the array functions the reference uses in `nll_analysis`
 over the `dwmh_s1_*` entry points of include/deepwmh_b200.h.  Inputs may be numpy arrays or CUDA tensors [X, Y, Z];
 results are fp32 CUDA tensors.  There is no CPU path: every function needs the library and a GPU.
 
-Not built: the Otsu branches (`apply_otsu`, `nll(use_mask=True)` -- skimage), the histogram / threshold search and the
-NIfTI / plot output.
+`threshold_otsu` restates skimage's published 256-bin algorithm (skimage is not vendored by the reference; that piece is
+`parity unpinned`).  Not built: `nll(use_mask=True)`, the histogram-curve threshold search and the NIfTI / plot output.
 """
 from __future__ import annotations
 
@@ -246,6 +246,91 @@ def component_filtering(mask: Array, voxel_size: Sequence[float], return_type: s
     with torch.cuda.device(m.device):
         _lib.check(lib.dwmh_s1_component_filtering(device, _ptr(m), X, Y, Z, vs, _ptr(out), _ptr(ws), _stream(device)))
     return out
+
+
+def minmax(data: Array, mask: Optional[Array] = None, device: int = 0) -> Tuple[float, float]:
+    lib = _lib.load()
+    x = _dev(data, device)
+    m = _dev(mask, device) if mask is not None else None
+    ws = torch.empty(2, dtype=torch.int32, device=x.device)
+    out = (C.c_float * 2)()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dwmh_s1_minmax(device, _ptr(x), _ptr(m), x.numel(), _ptr(ws), out, _stream(device)))
+    return float(out[0]), float(out[1])
+
+
+def histogram(data: Array, bin_edges: np.ndarray, mask: Optional[Array] = None, fill_value: Optional[float] = None,
+              device: int = 0) -> np.ndarray:
+    """numpy.histogram(values, bins=bin_edges) for equal-width edges; values = data[mask > 0.5], or
+    np.where(mask < 0.5, fill_value, data) when fill_value is given.  -> int64 counts on the host."""
+    lib = _lib.load()
+    x = _dev(data, device)
+    m = _dev(mask, device) if mask is not None else None
+    edges = torch.from_numpy(np.ascontiguousarray(bin_edges, dtype=np.float64)).to(x.device)
+    nbins = int(edges.numel()) - 1
+    counts = torch.empty(nbins, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dwmh_s1_histogram(device, _ptr(x), _ptr(m), x.numel(), int(fill_value is not None),
+                                         float(fill_value if fill_value is not None else 0.0), _ptr(edges), nbins, _ptr(counts), _stream(device)))
+    return counts.cpu().numpy()
+
+
+def _otsu_from_histogram(counts: np.ndarray, bin_edges: np.ndarray) -> float:
+    """The scan of skimage.filters.threshold_otsu: maximise the between-class variance over the 255 cut points."""
+    counts = counts.astype(np.float64)
+    centers = (bin_edges[:-1] + bin_edges[1:]) / 2.0
+    w1 = np.cumsum(counts)
+    w2 = np.cumsum(counts[::-1])[::-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m1 = np.cumsum(counts * centers) / w1
+        m2 = (np.cumsum((counts * centers)[::-1]) / w2[::-1])[::-1]
+    var12 = w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2
+    return float(centers[int(np.argmax(var12))])
+
+
+def threshold_otsu(image: Array, nbins: int = 256, mask: Optional[Array] = None, fill_value: Optional[float] = None,
+                   device: int = 0) -> float:
+    """skimage.filters.threshold_otsu(values), values = image (mask None), image[mask > 0.5] (`otsu_thresholding`,
+    image_ops.py:308-323) or np.where(mask < 0.5, fill_value, image) (lesion_analysis.py:145)."""
+    x = _dev(image, device)
+    m = _dev(mask, device) if mask is not None else None
+    lo, hi = minmax(x, m, device)
+    if m is not None and fill_value is not None:
+        lo, hi = min(lo, float(np.float32(fill_value))), max(hi, float(np.float32(fill_value)))
+    if lo == hi:
+        return lo                                                     # a single intensity: skimage returns it
+    edges = np.linspace(lo, hi, nbins + 1)
+    return _otsu_from_histogram(histogram(x, edges, m, fill_value, device), edges)
+
+
+def otsu_thresholding(image: Array, mask: Optional[Array] = None, device: int = 0) -> Optional[float]:
+    """image_ops.py:308-323."""
+    if mask is not None and float(_dev(mask, device).gt(0.5).sum().item()) < 1:
+        return None
+    return threshold_otsu(image, mask=mask, device=device)
+
+
+def threshold_mask(data: Array, threshold: float, mul_mask: Optional[Array] = None, device: int = 0) -> torch.Tensor:
+    """np.where(data > threshold, 1, 0) [* mul_mask] as fp32."""
+    lib = _lib.load()
+    x = _dev(data, device)
+    mm = _dev(mul_mask, device) if mul_mask is not None else None
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dwmh_s1_threshold_mask(device, _ptr(x), float(threshold), _ptr(mm), _ptr(out), x.numel(), _stream(device)))
+    return out
+
+
+def valid_score_mask(x_prime_raw: Array, m_rough_brain: Array, apply_otsu: bool = True, device: int = 0):
+    """lesion_analysis.py:142-148: z-score the target over the rough brain mask, Otsu-threshold it (voxels outside the
+    brain set to the volume minimum), m_valid_score = m_rough_brain * m_otsu.  -> (x_prime z-scored, m_valid_score)."""
+    brain = _dev(m_rough_brain, device)
+    xp = z_score(x_prime_raw, brain, device=device)
+    if not apply_otsu:
+        return xp, brain.clone()
+    lo, _ = minmax(xp, None, device)
+    thr = threshold_otsu(xp, mask=brain, fill_value=lo, device=device)
+    return xp, threshold_mask(xp, thr, brain, device)
 
 
 def image_patch_size(physical_voxel_size: Sequence[float], physical_patch_size=(50, 50, 50)) -> List[int]:

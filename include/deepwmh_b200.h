@@ -163,6 +163,18 @@ int dwmh_s1_component_filtering_workspace(int32_t X, int32_t Y, int32_t Z, int64
 int dwmh_s1_component_filtering(int32_t device, const float* mask_dev, int32_t X, int32_t Y, int32_t Z, const double voxel_size[3],
                                 float* out_dev, void* workspace_dev, void* stream);
 
+/* Otsu support (skimage.filters.threshold_otsu as called at lesion_analysis.py:145-146, image_ops.py:308-323; skimage is not
+ * vendored: its published 256-bin algorithm is restated, the 256-entry scan runs on the host -- deepwmh_b200/stage1.py).
+ * dwmh_s1_minmax: min / max over mask > 0.5 (NULL = all voxels) -> host out[2]; workspace >= 8 bytes; synchronises.
+ * dwmh_s1_histogram: numpy.histogram binning for nbins equal-width bins given their nbins + 1 edges (device, float64):
+ *   bin i holds edges[i] <= v < edges[i+1], last bin closed, exact edge corrections.  Voxels with mask < 0.5 are skipped
+ *   (fill_outside = 0) or counted as fill_value (np.where(mask < 0.5, fill, x)).  counts_dev: uint64 [nbins].
+ * dwmh_s1_threshold_mask: out = (x > threshold) * mul_mask   (mul_mask may be NULL). */
+int dwmh_s1_minmax(int32_t device, const float* x_dev, const float* mask_dev, int64_t n, void* workspace_dev, float out_minmax[2], void* stream);
+int dwmh_s1_histogram(int32_t device, const float* x_dev, const float* mask_dev, int64_t n, int32_t fill_outside, float fill_value,
+                      const double* edges_dev, int32_t nbins, uint64_t* counts_dev, void* stream);
+int dwmh_s1_threshold_mask(int32_t device, const float* x_dev, float threshold, const float* mul_mask_dev, float* out_dev, int64_t n, void* stream);
+
 /* --- a6 end to end with HOST buffers (what predict_preprocessed_data_return_seg_and_softmax does):
  * raw fp32 volume [X][Y][Z] in host memory -> (optional z-score, mask_mode as above, <0 = skip)
  * -> tiled prediction -> host softmax fp32 [2][X][Y][Z] and seg uint8 [X][Y][Z].  H2D/D2H inside. */

@@ -188,6 +188,34 @@ def component_filtering(mask, voxel_size):
     return (total > 0.5).astype(np.float32)
 
 
+def threshold_otsu(values, nbins=256):
+    """skimage.filters.threshold_otsu (third-party, NOT vendored under /root/reference and absent here; scikit-image >= 0.16
+    published algorithm, PARITY UNPINNED): 256 equal-width bins over [min, max] (numpy.histogram), threshold = centre of
+    the bin that maximises the between-class variance w1 * w2 * (m1 - m2)^2; a constant image returns its value.
+    Reference call sites: lesion_analysis.py:90,145-146, image_ops.py:308-323."""
+    v = np.asarray(values, np.float64).reshape(-1)
+    if np.all(v == v[0]):
+        return float(v[0])
+    counts, edges = np.histogram(v, bins=nbins)
+    counts = counts.astype(np.float64)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    w1, w2 = np.cumsum(counts), np.cumsum(counts[::-1])[::-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        m1 = np.cumsum(counts * centers) / w1
+        m2 = (np.cumsum((counts * centers)[::-1]) / w2[::-1])[::-1]
+    return float(centers[int(np.argmax(w1[:-1] * w2[1:] * (m1[:-1] - m2[1:]) ** 2))])
+
+
+def valid_score_mask(x_prime_raw, brain, apply_otsu=True):
+    """lesion_analysis.py:142-148."""
+    x = z_score(x_prime_raw, brain)
+    b = (np.asarray(brain) >= 0.5)
+    if not apply_otsu:
+        return x, b.astype(np.float32)
+    thr = threshold_otsu(np.where(b, x, x.min()))
+    return x, (b * (x > thr)).astype(np.float32)
+
+
 def nll_anomaly_arrays(target, refs, brain, valid, patch, min_std=0.03, side="+", mean_correction=True):
     """The array part of nll_analysis, lesion_analysis.py:142-176 (after the masks are known)."""
     x_prime = tissue_min_fill(z_score(target, brain), brain)

@@ -134,6 +134,38 @@ def test_component_filtering_edge_cases(g, S):
         S.component_filtering(g["in_brain"], [1.0, 1.0, 1.0], return_type="int")
 
 
+def test_otsu_and_valid_score_mask(g, S):
+    """threshold_otsu restates skimage's published algorithm (skimage is not vendored: unpinned); the device histogram is
+    numpy.histogram bit for bit, so the threshold equals the numpy restatement on the same fp32 values exactly."""
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.normal(-1, 0.3, 40000), rng.normal(2, 0.5, 25000)]).astype(np.float32).reshape(50, 50, 26)
+    edges = np.linspace(float(x.min()), float(x.max()), 257)
+    assert np.array_equal(S.histogram(x, edges), np.histogram(x.astype(np.float64), bins=edges)[0])
+    assert S.minmax(x) == (float(x.min()), float(x.max()))
+    assert S.threshold_otsu(x) == I.threshold_otsu(x) and -0.5 < S.threshold_otsu(x) < 1.5
+    m = (rng.random(x.shape) > 0.4).astype(np.float32)
+    assert np.array_equal(S.histogram(x, edges, mask=m), np.histogram(x[m > 0.5].astype(np.float64), bins=edges)[0])
+    assert np.array_equal(S.histogram(x, edges, mask=m, fill_value=float(x.min())),
+                          np.histogram(np.where(m > 0.5, x, x.min()).astype(np.float64), bins=edges)[0])
+    assert S.otsu_thresholding(x, m) == I.threshold_otsu(x[m > 0.5])
+    assert S.otsu_thresholding(x, np.zeros_like(m)) is None
+    assert S.threshold_otsu(np.full((4, 4, 4), 3.5, np.float32)) == 3.5
+    # values exactly on bin edges and the closed last bin
+    e8 = np.linspace(0.0, 8.0, 9)
+    v = np.array([0, 1, 1, 2, 7.9999995, 8, 8, 3.5, -1, 9], np.float32).reshape(1, 2, 5)
+    assert np.array_equal(S.histogram(v, e8), np.histogram(v.astype(np.float64), bins=e8)[0])
+    # lesion_analysis.py:142-148 on the fixture's raw target
+    xp, valid = S.valid_score_mask(g["in_target"], g["in_brain"])
+    xo, vo = I.valid_score_mask(g["in_target"], g["in_brain"])
+    assert np.allclose(h(xp), xo, rtol=1e-5, atol=1e-5)
+    xh, b = h(xp), g["in_brain"] >= 0.5
+    thr = I.threshold_otsu(np.where(b, xh, xh.min()))                 # the restatement on the device's own fp32 z-scores
+    assert np.array_equal(h(valid), (b * (xh > np.float32(thr))).astype(np.float32))
+    assert (h(valid) != vo).mean() < 1e-2 and 0 < h(valid).sum() < g["in_brain"].sum()
+    _, allv = S.valid_score_mask(g["in_target"], g["in_brain"], apply_otsu=False)
+    assert np.array_equal(h(allv), (g["in_brain"] >= 0.5).astype(np.float32))
+
+
 def test_batched_case_launches_equal_the_function_by_function_path(g, S):
     """dwmh_s1_zscore_batch / dwmh_s1_local_mean_align (whole case per launch) against z_score / mean_std_grid /
     align_local_mean_ called volume by volume."""
