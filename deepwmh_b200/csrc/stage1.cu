@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256) s1_median_kernel(const float* __restrict_
   out[((int64_t)gx * Y + gy) * Z + gz] = key2f(key);
 }
 
-// Compile-time odd windows up to 27 values (3x3x3 = the 1 mm isotropic case; 3x3 slices for thick-slice data): the
+// Compile-time windows up to 65 values (3x3x3 = the 1 mm isotropic case; k x k slices for thick-slice data): the
 // window goes through registers once and the median is found by forgetful selection -- of N/2 + 2 values neither the
 // minimum nor the maximum can be the median, so drop both, add the next value, repeat -- with min/max exchanges only
 // (~155 exchanges for N = 27 instead of 32 x 27 compares).
@@ -401,20 +401,26 @@ __device__ __forceinline__ void minmax_ends(uint32_t (&v)[W]) {     // min of v[
 #pragma unroll
   for (int i = S / 2; i < S - 1; ++i) { const uint32_t lo = min(v[i], v[S - 1]), hi = max(v[i], v[S - 1]); v[i] = lo; v[S - 1] = hi; }
 }
-template <int S, int W, int N, int KY, int KZ>
+template <int KY, int KZ, int N>
+__device__ __forceinline__ uint32_t window_key(const uint32_t* __restrict__ base, int e_ty_tz_unused, int ty, int tz, int e) {
+  return e < N ? base[((e / (KY * KZ)) * ty + (e / KZ) % KY) * tz + e % KZ] : 0xffffffffu;   // e >= N: the +inf pad of even windows
+}
+template <int S, int W, int NP, int N, int KY, int KZ>
 __device__ __forceinline__ void forget_step(uint32_t (&v)[W], const uint32_t* __restrict__ base, int ty, int tz) {
   if constexpr (S >= 3) {
-    constexpr int e = N - (S - 2);                                   // index of the window value added at this size
-    if constexpr (S < W) v[0] = base[((e / (KY * KZ)) * ty + (e / KZ) % KY) * tz + e % KZ];
+    constexpr int e = NP - (S - 2);                                  // index of the window value added at this size
+    if constexpr (S < W) v[0] = window_key<KY, KZ, N>(base, 0, ty, tz, e);
     minmax_ends<S, W>(v);
-    forget_step<S - 1, W, N, KY, KZ>(v, base, ty, tz);
+    forget_step<S - 1, W, NP, N, KY, KZ>(v, base, ty, tz);
   }
 }
 
+// Even windows (4x4x4, 6x6 slices ...): scipy takes rank N / 2 (the upper median); padding the window with one +inf key
+// makes it odd without moving that rank, so the same selection applies.
 template <int KX, int KY, int KZ>
 __global__ void __launch_bounds__(256) s1_median_small_kernel(const float* __restrict__ in, float* __restrict__ out, int X, int Y, int Z) {
-  constexpr int N = KX * KY * KZ, W = N / 2 + 2;
-  static_assert(N % 2 == 1 && N >= 3 && N <= 27, "odd windows of 3..27 values");
+  constexpr int N = KX * KY * KZ, NP = N | 1, W = NP / 2 + 2;
+  static_assert(N >= 3 && N <= 65, "windows of 3..65 values");
   constexpr int tx = MT_X + KX - 1, ty = MT_Y + KY - 1, tz = MT_Z + KZ - 1;
   __shared__ uint32_t tile[tx * ty * tz];
   const int bz = blockIdx.x * MT_Z, by = blockIdx.y * MT_Y, bx = blockIdx.z * MT_X;
@@ -433,9 +439,16 @@ __global__ void __launch_bounds__(256) s1_median_small_kernel(const float* __res
   const uint32_t* base = tile + (lx * ty + ly) * tz + lz;
   uint32_t v[W];
 #pragma unroll
-  for (int e = 0; e < W; ++e) v[e] = base[((e / (KY * KZ)) * ty + (e / KZ) % KY) * tz + e % KZ];
-  forget_step<W, W, N, KY, KZ>(v, base, ty, tz);                     // ends with the median of the last three in v[1]
+  for (int e = 0; e < W; ++e) v[e] = window_key<KY, KZ, N>(base, 0, ty, tz, e);
+  forget_step<W, W, NP, N, KY, KZ>(v, base, ty, tz);                 // ends with the median of the last three in v[1]
   out[((int64_t)gx * Y + gy) * Z + gz] = key2f(v[1]);
+}
+
+template <int KX, int KY, int KZ>
+bool median_small_launch(int kx, int ky, int kz, dim3 grid, cudaStream_t st, const float* in, float* out, int X, int Y, int Z) {
+  if (kx != KX || ky != KY || kz != KZ) return false;
+  s1_median_small_kernel<KX, KY, KZ><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
+  return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -731,11 +744,13 @@ extern "C" int dwmh_s1_median_filter(int32_t device, const float* in, float* out
   dim3 grid((Z + MT_Z - 1) / MT_Z, (Y + MT_Y - 1) / MT_Y, (X + MT_X - 1) / MT_X);
   if (grid.y > 65535 || grid.z > 65535) return fail("dwmh_s1_median_filter: volume too large");
   cudaStream_t st = (cudaStream_t)stream_;
-  if (kx == 3 && ky == 3 && kz == 3) s1_median_small_kernel<3, 3, 3><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
-  else if (kx == 1 && ky == 3 && kz == 3) s1_median_small_kernel<1, 3, 3><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
-  else if (kx == 3 && ky == 1 && kz == 3) s1_median_small_kernel<3, 1, 3><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
-  else if (kx == 3 && ky == 3 && kz == 1) s1_median_small_kernel<3, 3, 1><<<grid, 256, 0, st>>>(in, out, X, Y, Z);
-  else s1_median_kernel<<<grid, 256, smem, st>>>(in, out, X, Y, Z, kx, ky, kz);
+  // register-resident selection for the windows median_3mm produces at common resolutions: 1 mm isotropic (3x3x3),
+  // ~0.75 mm (4x4x4), thick slices with 1 / 0.75 / 0.6 / 0.5 mm in-plane (3x3, 4x4, 5x5, 6x6 across any axis)
+#define MS(a, b, c) median_small_launch<a, b, c>(kx, ky, kz, grid, st, in, out, X, Y, Z)
+  const bool done = MS(3, 3, 3) || MS(4, 4, 4) || MS(1, 3, 3) || MS(3, 1, 3) || MS(3, 3, 1) || MS(1, 4, 4) || MS(4, 1, 4) || MS(4, 4, 1) ||
+                    MS(1, 5, 5) || MS(5, 1, 5) || MS(5, 5, 1) || MS(1, 6, 6) || MS(6, 1, 6) || MS(6, 6, 1);
+#undef MS
+  if (!done) s1_median_kernel<<<grid, 256, smem, st>>>(in, out, X, Y, Z, kx, ky, kz);
   S1_CU(cudaGetLastError());
   return 0;
 }

@@ -90,7 +90,10 @@ def test_median_3mm_bit_exact_with_reference_fixture(g, S, tag):
 
 def test_median_filter_edge_cases(S):
     rng = np.random.default_rng(3)
-    for shape, ks in (((1, 1, 1), [3, 3, 3]), ((5, 3, 70), [1, 1, 1]), ((7, 9, 33), [9, 2, 5]), ((2, 70, 3), [3, 7, 1])):
+    for shape, ks in (((1, 1, 1), [3, 3, 3]), ((5, 3, 70), [1, 1, 1]), ((7, 9, 33), [9, 2, 5]), ((2, 70, 3), [3, 7, 1]),
+                      # register-resident selection: odd and even (+inf padded) windows, every slice orientation
+                      ((9, 21, 40), [4, 4, 4]), ((6, 37, 45), [1, 6, 6]), ((33, 5, 41), [6, 1, 6]), ((35, 38, 4), [6, 6, 1]),
+                      ((30, 3, 33), [5, 1, 5]), ((17, 18, 5), [4, 4, 1]), ((3, 30, 31), [1, 5, 5]), ((20, 20, 20), [1, 3, 3])):
         x = rng.normal(size=shape).astype(np.float32)
         x[rng.random(shape) > 0.7] = 0.0                              # ties with the zero padding
         x[rng.random(shape) > 0.9] *= -1.0

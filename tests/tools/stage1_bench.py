@@ -64,7 +64,9 @@ def main():
     row("mean_std_grid (3 kernels)", lambda: S.mean_std_grid(zt, patch, mask=valid), V * 4 * (2 + 2))
     row("group mean/std + nll, k=%d" % K, lambda: S.nll(zt, zr, min_std=0.03, side="+", return_all=True, mul_mask=valid), V * 4 * (K + 2 + 3))
     row("median 3x3x3", lambda: S.median_3mm(an, [1.0, 1.0, 1.0]), V * 4 * 2)
-    row("median 6x5x3", lambda: S.median_filter(an, [6, 5, 3]), V * 4 * 2)
+    row("median 4x4x4", lambda: S.median_filter(an, [4, 4, 4]), V * 4 * 2)
+    row("median 6x6 slices", lambda: S.median_filter(an, [6, 6, 1]), V * 4 * 2)
+    row("median 6x5x3 (generic rank search)", lambda: S.median_filter(an, [6, 5, 3]), V * 4 * 2)
     row("component_filtering (3 orientations, 16 launches)", lambda: S.component_filtering(valid, [1.0, 1.0, 1.0]), V * 4 * 2)
     row("anomaly map end to end (k=%d)" % K, lambda: S.nll_anomaly_map(tgt, refs, brain, valid, intensity_prior="+"), V * 4 * (K + 1) * 2)
     out = {"shape": shape, "k_refs": K, "hbm_peak_GBps": peak, "l2": "256 MiB buffer written before every timed call", "rows": rows}
