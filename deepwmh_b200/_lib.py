@@ -59,6 +59,9 @@ SYMBOLS = {
     "dwmh_s1_minmax": (C.c_int, [C.c_int32, _P, _P, C.c_int64, _P, C.POINTER(C.c_float), _P]),
     "dwmh_s1_histogram": (C.c_int, [C.c_int32, _P, _P, C.c_int64, C.c_int32, C.c_float, _P, C.c_int32, _P, _P]),
     "dwmh_s1_threshold_mask": (C.c_int, [C.c_int32, _P, C.c_float, _P, _P, C.c_int64, _P]),
+    "dwmh_s1_masked_sums": (C.c_int, [C.c_int32, C.POINTER(_P), C.c_int32, _P, C.c_int64, C.c_int32, _P, C.POINTER(C.c_double), _P]),
+    "dwmh_s1_label_vote": (C.c_int, [C.c_int32, C.POINTER(_P), C.c_int32, C.c_int32, _P, _P, C.c_int64, _P]),
+    "dwmh_s1_apply_priors": (C.c_int, [C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int64, _P]),
     "dwmh_predict_volume_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
                                            C.c_int32, C.c_int32, _P, _P, _P]),
     "dwmh_forward_patches": (C.c_int, [_P, _P, C.c_int32, _P, _P]),

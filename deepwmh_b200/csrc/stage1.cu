@@ -57,7 +57,7 @@ __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i
 // ---------------------------------------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(256) s1_stats_kernel(VolPtrs vols, const float* __restrict__ mask,
-                                                       int64_t n, double* __restrict__ ws) {
+                                                       int64_t n, double* __restrict__ ws, int positive_only = 0) {
   const float* __restrict__ x = vols.p[blockIdx.y];
   double* acc = ws + (size_t)blockIdx.y * ZS_SLOT;
   int* minord = reinterpret_cast<int*>(acc + 4);
@@ -72,11 +72,11 @@ __global__ void __launch_bounds__(256) s1_stats_kernel(VolPtrs vols, const float
     const float vv[4] = {v.x, v.y, v.z, v.w}, mm[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (mm[j] > 0.5f) { s += vv[j]; ss += (double)vv[j] * vv[j]; cnt += 1.0; mn = min(mn, f2ord(vv[j])); }
+      if (mm[j] > 0.5f && (!positive_only || vv[j] > 0.f)) { s += vv[j]; ss += (double)vv[j] * vv[j]; cnt += 1.0; mn = min(mn, f2ord(vv[j])); }
   }
   for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
     const float v = x[i];
-    if (!mask || mask[i] > 0.5f) { s += v; ss += (double)v * v; cnt += 1.0; mn = min(mn, f2ord(v)); }
+    if ((!mask || mask[i] > 0.5f) && (!positive_only || v > 0.f)) { s += v; ss += (double)v * v; cnt += 1.0; mn = min(mn, f2ord(v)); }
   }
   s = warp_sum_d(s); ss = warp_sum_d(ss); cnt = warp_sum_d(cnt);
   mn = __reduce_min_sync(0xffffffffu, mn);
@@ -568,6 +568,49 @@ __global__ void __launch_bounds__(256) s1_threshold_kernel(const float* __restri
     out[i] = (x[i] > thr ? 1.f : 0.f) * (mul ? mul[i] : 1.f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tissue priors of nll_analysis (lesion_analysis.py:213-243): majority vote over the K registered label maps
+// (average_contiguous_labels, image_ops.py:23-38: per-voxel argmax of the label histogram, first maximum wins), the
+// "labelled as tissue by more than half of the references" mask, and their application to the anomaly score.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int S1_MAX_LABELS = 16;
+__global__ void __launch_bounds__(256) s1_label_vote_kernel(RefPtrs labels, int K, int nch, float* __restrict__ avg_label,
+                                                            float* __restrict__ tissue_majority, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned long long votes = 0ull;                                 // 16 x 4-bit... K <= 32 needs 6 bits: two words of 8 x 8-bit counters
+    unsigned long long votes_hi = 0ull;
+    int tissue = 0;
+    for (int k = 0; k < K; ++k) {
+      const float t = __ldg(labels.p[k] + i);
+      const int c = (int)t;                                          // label.astype('int')
+      if (c >= 0 && c < 8) votes += 1ull << (8 * c);
+      else if (c >= 8 && c < nch) votes_hi += 1ull << (8 * (c - 8));
+      tissue += t > 0.5f ? 1 : 0;
+    }
+    int best = 0, best_n = -1;
+    for (int c = 0; c < nch; ++c) {
+      const int v = (int)(((c < 8 ? votes >> (8 * c) : votes_hi >> (8 * (c - 8)))) & 0xffull);
+      if (v > best_n) { best_n = v; best = c; }
+    }
+    if (avg_label) avg_label[i] = (float)best;
+    if (tissue_majority) tissue_majority[i] = (2 * tissue > K) ? 1.f : 0.f;   // tissue_sum > sample_size / 2
+  }
+}
+
+// stage 1: a *= (avg_label > 0.5)                                           (:216)
+// stage 2: a = (1.5 < avg_label < 2.5 ? a_median : a) * tissue_majority      (:232-243)
+__global__ void __launch_bounds__(256) s1_apply_priors_kernel(float* __restrict__ a, const float* __restrict__ a_median,
+                                                              const float* __restrict__ avg_label, const float* __restrict__ tissue_majority,
+                                                              int stage, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float l = avg_label[i];
+    if (stage == 1) a[i] = l > 0.5f ? a[i] : 0.f * a[i];
+    else a[i] = ((l > 1.5f && l < 2.5f) ? a_median[i] : a[i]) * tissue_majority[i];
+  }
+}
+
 int geom(int X, int Y, int Z, const int32_t patch[3], GridGeom* q) {
   if (X <= 0 || Y <= 0 || Z <= 0) return fail("mean_std_grid: empty volume");
   q->X = X; q->Y = Y; q->Z = Z;
@@ -837,6 +880,54 @@ extern "C" int dwmh_s1_threshold_mask(int32_t device, const float* x, float thre
   if (!x || !out) return fail("dwmh_s1_threshold_mask: null argument");
   S1_CU(cudaSetDevice(device));
   s1_threshold_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x, threshold, mul_mask, out, n);
+  S1_CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwmh_s1_masked_sums(int32_t device, const float* const* xs, int32_t nvol, const float* mask, int64_t n, int32_t positive_only,
+                                   void* workspace, double* out_host, void* stream_) {
+  if (!xs || !workspace || !out_host) return fail("dwmh_s1_masked_sums: null argument");
+  if (nvol <= 0 || nvol > S1_MAX_VOLS) return fail("dwmh_s1_masked_sums: %d volumes (1..%d supported)", nvol, S1_MAX_VOLS);
+  if (n <= 0) return fail("dwmh_s1_masked_sums: empty volume");
+  VolPtrs vols{};
+  uintptr_t al = (uintptr_t)mask;
+  for (int i = 0; i < nvol; ++i) { if (!xs[i]) return fail("dwmh_s1_masked_sums: xs[%d] is null", i); vols.p[i] = const_cast<float*>(xs[i]); al |= (uintptr_t)xs[i]; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  S1_CU(cudaSetDevice(device));
+  double* ws = (double*)workspace;
+  S1_CU(cudaMemsetAsync(ws, 0, (size_t)nvol * ZS_SLOT * sizeof(double), st));
+  S1_CU(cudaMemset2DAsync((char*)workspace + 32, ZS_SLOT * sizeof(double), 0x7f, 4, nvol, st));
+  const dim3 grid((grid_for(device) + nvol - 1) / nvol, nvol);
+  if ((al & 15) == 0) s1_stats_kernel<true><<<grid, 256, 0, st>>>(vols, mask, n, ws, positive_only);
+  else s1_stats_kernel<false><<<grid, 256, 0, st>>>(vols, mask, n, ws, positive_only);
+  S1_CU(cudaGetLastError());
+  double h[S1_MAX_VOLS * ZS_SLOT];
+  S1_CU(cudaMemcpyAsync(h, ws, (size_t)nvol * ZS_SLOT * sizeof(double), cudaMemcpyDeviceToHost, st));
+  S1_CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < nvol; ++i) for (int j = 0; j < 3; ++j) out_host[i * 3 + j] = h[i * ZS_SLOT + j];
+  return 0;
+}
+
+extern "C" int dwmh_s1_label_vote(int32_t device, const float* const* labels, int32_t k, int32_t num_labels, float* averaged_label,
+                                  float* tissue_majority, int64_t n, void* stream_) {
+  if (!labels) return fail("dwmh_s1_label_vote: null argument");
+  if (k <= 0 || k > S1_MAX_REFS) return fail("dwmh_s1_label_vote: k = %d label maps (1..%d supported)", k, S1_MAX_REFS);
+  if (num_labels < 1 || num_labels > S1_MAX_LABELS) return fail("dwmh_s1_label_vote: %d label ids (1..%d supported)", num_labels, S1_MAX_LABELS);
+  RefPtrs rp{};
+  for (int i = 0; i < k; ++i) { if (!labels[i]) return fail("dwmh_s1_label_vote: labels[%d] is null", i); rp.p[i] = labels[i]; }
+  S1_CU(cudaSetDevice(device));
+  s1_label_vote_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(rp, k, num_labels, averaged_label, tissue_majority, n);
+  S1_CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwmh_s1_apply_priors(int32_t device, float* anomaly, const float* anomaly_median, const float* averaged_label,
+                                    const float* tissue_majority, int32_t stage, int64_t n, void* stream_) {
+  if (!anomaly || !averaged_label) return fail("dwmh_s1_apply_priors: null argument");
+  if (stage != 1 && stage != 2) return fail("dwmh_s1_apply_priors: stage must be 1 or 2");
+  if (stage == 2 && (!anomaly_median || !tissue_majority)) return fail("dwmh_s1_apply_priors: stage 2 needs the median-filtered score and the tissue mask");
+  S1_CU(cudaSetDevice(device));
+  s1_apply_priors_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(anomaly, anomaly_median, averaged_label, tissue_majority, stage, n);
   S1_CU(cudaGetLastError());
   return 0;
 }

@@ -364,3 +364,116 @@ def nll_anomaly_map(x_prime: Array, x_refs: Sequence[Array], m_rough_brain: Arra
     if with_reference_scores:
         out["reference_anomalies"] = [nll(r, refs, min_std=min_std, side=intensity_prior, mul_mask=valid, device=device) for r in refs]
     return out
+
+
+def masked_sums(volumes: Sequence[torch.Tensor], mask: Optional[Array] = None, positive_only: bool = False) -> np.ndarray:
+    """{sum, sum of squares, count} per volume over mask > 0.5 (and value > 0), one launch -> float64 [nvol, 3] on the host."""
+    lib = _lib.load()
+    dev = volumes[0].device
+    m = _dev(mask, dev.index) if mask is not None else None
+    ws = torch.empty(8 * len(volumes), dtype=torch.float64, device=dev)
+    out = (C.c_double * (3 * len(volumes)))()
+    ptrs = (C.c_void_p * len(volumes))(*[v.data_ptr() for v in volumes])
+    with torch.cuda.device(dev):
+        _lib.check(lib.dwmh_s1_masked_sums(dev.index, ptrs, len(volumes), _ptr(m), volumes[0].numel(), int(bool(positive_only)), _ptr(ws),
+                                           out, _stream(dev.index)))
+    return np.array(out, dtype=np.float64).reshape(len(volumes), 3)
+
+
+def hist_curve(data: Array, bins: np.ndarray, log_y: bool = False, mask: Optional[Array] = None, device: int = 0):
+    """lesion_analysis.py:40-50 (equal-width `bins` edges)."""
+    hist = histogram(data, bins, mask=mask, device=device).astype(np.int64)
+    bins = np.asarray(bins, np.float64)
+    centers = (bins[:-1] + bins[1:]) / 2
+    if log_y:
+        hist = np.where(hist == 0, 0.001, hist)
+        hist = np.log10(hist)
+        hist = np.where(hist < 0, 0, hist)
+    return centers, hist
+
+
+def histogram_analysis(a_prime: Array, a_refs: Sequence[Array], bins: Optional[np.ndarray] = None, mask: Optional[Array] = None, device: int = 0):
+    """lesion_analysis.py:52-82: log-histogram curves of the target's anomaly score and of every reference's; default bins =
+    400 bins of width (mean over references of the mean positive masked score) / 4."""
+    if not isinstance(a_refs, (list, tuple)):
+        a_refs = [a_refs]
+    refs = [_dev(r, device) for r in a_refs]
+    if bins is None:
+        assert mask is not None, 'must provide mask when "bins" is None.'
+        sums = masked_sums(refs, mask, positive_only=True)
+        ref_means = sums[:, 0] / sums[:, 2]
+        bin_width = ref_means.mean() / 4
+        num_bins = 400
+        bins = np.linspace(0.0, 0.0 + num_bins * bin_width, num=num_bins + 1)
+    x, y = hist_curve(a_prime, bins, log_y=True, device=device)
+    rs = [hist_curve(r, bins, log_y=True, device=device)[1] for r in refs]
+    r = np.zeros_like(x)
+    for r0 in rs:
+        r = r + r0
+    return x, y, r / len(rs), rs
+
+
+def anomaly_threshold_from_curves(curve_x: np.ndarray, curve_rs: Sequence[np.ndarray]) -> float:
+    """lesion_analysis.py:194-207: per reference, the right-most histogram bin whose log-count exceeds 0.01; the initial
+    segmentation threshold is the median of those positions."""
+    zero_crossings = []
+    for rs in curve_rs:
+        for j in range(len(rs) - 1, 0, -1):
+            if rs[j] > 0.01:
+                zero_crossings.append(curve_x[j])
+                break
+    return float(np.median(np.sort(zero_crossings)))
+
+
+def label_vote(labels: Sequence[Array], device: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """average_contiguous_labels (image_ops.py:23-38) and the tissue majority mask (lesion_analysis.py:238-242)."""
+    lib = _lib.load()
+    ls = [_dev(l, device) for l in labels]
+    num = 1 + max(int(minmax(l, None, device)[1]) for l in ls)
+    avg, tissue = torch.empty_like(ls[0]), torch.empty_like(ls[0])
+    ptrs = (C.c_void_p * len(ls))(*[l.data_ptr() for l in ls])
+    with torch.cuda.device(ls[0].device):
+        _lib.check(lib.dwmh_s1_label_vote(device, ptrs, len(ls), num, _ptr(avg), _ptr(tissue), avg.numel(), _stream(device)))
+    return avg, tissue
+
+
+def average_contiguous_labels(labels: Sequence[Array], device: int = 0) -> torch.Tensor:
+    return label_vote(labels, device)[0]
+
+
+def apply_priors_(anomaly: torch.Tensor, averaged_label: torch.Tensor, tissue_majority: Optional[torch.Tensor] = None,
+                  anomaly_median: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Stage 1 (no median given): anomaly *= (averaged_label > 0.5).  Stage 2: cerebellum / brainstem voxels take the
+    median-filtered score, everything is masked by the tissue majority vote.  In place."""
+    lib = _lib.load()
+    dev = anomaly.device
+    with torch.cuda.device(dev):
+        _lib.check(lib.dwmh_s1_apply_priors(dev.index, _ptr(anomaly), _ptr(anomaly_median), _ptr(averaged_label), _ptr(tissue_majority),
+                                            1 if anomaly_median is None else 2, anomaly.numel(), _stream(dev.index)))
+    return anomaly
+
+
+def nll_analysis_arrays(x: Array, x_refs: Sequence[Array], ref_label1: Sequence[Array], ref_label2: Sequence[Array],
+                        physical_voxel_size: Sequence[float], apply_otsu: bool = True, intensity_prior: Optional[str] = None,
+                        mean_correction: bool = True, device: int = 0):
+    """`nll_analysis` (lesion_analysis.py:115-281) on arrays instead of NIfTI paths: x = case_info['x'], x_refs = ['r'],
+    ref_label1 = ['m'] (brain masks of the references), ref_label2 = ['y'] (tissue labels 0..3).
+    -> (anomaly, m_valid_score, curve_x, curve_y, curve_r, anomaly_threshold) as the reference returns them (volumes as fp32
+    CUDA tensors), plus a dict with normalized_input / local_mean / mean / std / averaged_label / rough_brain."""
+    assert intensity_prior in [None, "+", "-"], 'Unknown intensity prior "%s".' % str(intensity_prior)
+    vox = [float(v) for v in physical_voxel_size]
+    patch = image_patch_size(vox)
+    m_i = [threshold_mask(l, 0.5, device=device) for l in ref_label1]
+    m_rough_brain = threshold_mask(group_mean(m_i, device=device), 0.5, device=device)
+    _, m_valid = valid_score_mask(x, m_rough_brain, apply_otsu=apply_otsu, device=device)
+    r = nll_anomaly_map(x, x_refs, m_rough_brain, m_valid, vox, intensity_prior=intensity_prior, mean_correction=mean_correction,
+                        min_std=0.03, image_patch=patch, with_reference_scores=True, apply_component_filtering=True, device=device)
+    anomaly = r["anomaly"]
+    curve_x, curve_y, curve_r, curve_rs = histogram_analysis(anomaly, r["reference_anomalies"], mask=m_valid, device=device)
+    thr = anomaly_threshold_from_curves(curve_x, curve_rs)
+    averaged_label, tissue = label_vote(ref_label2, device=device)
+    apply_priors_(anomaly, averaged_label)
+    apply_priors_(anomaly, averaged_label, tissue, median_3mm(anomaly, vox, device=device))
+    extras = {"normalized_input": r["normalized_input"], "local_mean": r["local_mean"], "mean": r["mean"], "std": r["std"],
+              "averaged_label": averaged_label, "rough_brain": m_rough_brain, "curve_rs": curve_rs}
+    return anomaly, m_valid, curve_x, curve_y, curve_r, thr, extras

@@ -175,6 +175,21 @@ int dwmh_s1_histogram(int32_t device, const float* x_dev, const float* mask_dev,
                       const double* edges_dev, int32_t nbins, uint64_t* counts_dev, void* stream);
 int dwmh_s1_threshold_mask(int32_t device, const float* x_dev, float threshold, const float* mul_mask_dev, float* out_dev, int64_t n, void* stream);
 
+/* Histogram-curve and tissue-prior steps of nll_analysis (lesion_analysis.py:52-82,188-243).
+ * dwmh_s1_masked_sums: {sum, sum of squares, count} of nvol <= 33 volumes over mask > 0.5 (and v > 0 if positive_only), one
+ *   launch; out_host: double [nvol][3]; workspace >= 64 * nvol bytes; synchronises.  (bin width of histogram_analysis :64-66)
+ * dwmh_s1_label_vote: average_contiguous_labels (image_ops.py:23-38; per-voxel argmax of the label histogram over the k maps,
+ *   first maximum wins, label ids < num_labels <= 16) and tissue_majority = (#maps with label > 0.5) > k / 2 (:238-242);
+ *   labels = HOST array of k device pointers to fp32 label maps; either output may be NULL.
+ * dwmh_s1_apply_priors: stage 1: anomaly *= (averaged_label > 0.5) (:216);
+ *   stage 2: anomaly = (1.5 < averaged_label < 2.5 ? anomaly_median : anomaly) * tissue_majority (:232-243).  In place. */
+int dwmh_s1_masked_sums(int32_t device, const float* const* xs, int32_t nvol, const float* mask_dev, int64_t n, int32_t positive_only,
+                        void* workspace_dev, double* out_host, void* stream);
+int dwmh_s1_label_vote(int32_t device, const float* const* labels, int32_t k, int32_t num_labels, float* averaged_label_dev,
+                       float* tissue_majority_dev, int64_t n, void* stream);
+int dwmh_s1_apply_priors(int32_t device, float* anomaly_dev, const float* anomaly_median_dev, const float* averaged_label_dev,
+                         const float* tissue_majority_dev, int32_t stage, int64_t n, void* stream);
+
 /* --- a6 end to end with HOST buffers (what predict_preprocessed_data_return_seg_and_softmax does):
  * raw fp32 volume [X][Y][Z] in host memory -> (optional z-score, mask_mode as above, <0 = skip)
  * -> tiled prediction -> host softmax fp32 [2][X][Y][Z] and seg uint8 [X][Y][Z].  H2D/D2H inside. */

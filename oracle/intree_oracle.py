@@ -225,3 +225,44 @@ def nll_anomaly_arrays(target, refs, brain, valid, patch, min_std=0.03, side="+"
         x_i = [x - mean_std_grid(x, patch, mask=valid)[0] + mu_p for x in x_i]
     an, xm, xs = nll(x_prime, x_i, min_std=min_std, side=side, return_all=True)
     return {"x_prime": x_prime, "local_mu": mu_p, "anomaly": an * valid, "mean": xm, "std": xs, "refs": x_i}
+
+
+def average_contiguous_labels(labels):
+    """image_ops.py:23-38: voxelwise majority label over the maps (argmax of the label histogram: first maximum)."""
+    n = 1 + max(int(np.max(l)) for l in labels)
+    votes = np.stack([sum((np.asarray(l).astype("int") == c).astype(np.float32) for l in labels) for c in range(n)])
+    return np.argmax(votes, axis=0)
+
+
+def hist_curve(data, bins, log_y=False):
+    """lesion_analysis.py:40-50."""
+    hist, edges = np.histogram(data, bins=bins)
+    centers = (edges[:-1] + edges[1:]) / 2
+    if log_y:
+        hist = np.log10(np.where(hist == 0, 0.001, hist))
+        hist = np.where(hist < 0, 0, hist)
+    return centers, hist
+
+
+def nll_analysis_arrays(x, refs, label1, label2, voxel_size, intensity_prior=None, apply_otsu=False):
+    """nll_analysis, lesion_analysis.py:115-281, on arrays -> (anomaly, m_valid, curve_x, curve_y, curve_r, threshold, extras)."""
+    vox = [float(v) for v in voxel_size]
+    patch = [int(np.ceil(50.0 / v)) for v in vox]
+    rough = (np.mean(np.stack([(np.asarray(m) > 0.5).astype(np.float32) for m in label1]), axis=0) > 0.5).astype(np.float32)
+    _, valid = valid_score_mask(x, rough, apply_otsu)
+    r = nll_anomaly_arrays(x, refs, rough, valid, patch, min_std=0.03, side=intensity_prior)
+    anomaly = r["anomaly"] * component_filtering(valid, vox)
+    an_refs = [nll(s, r["refs"], min_std=0.03, side=intensity_prior) * valid for s in r["refs"]]
+    means = [a[(valid > 0.5) & (a > 0)].mean() for a in an_refs]
+    bins = np.linspace(0.0, 400 * (np.mean(means) / 4), 401)
+    cx, cy = hist_curve(anomaly, bins, True)
+    rs = [hist_curve(a, bins, True)[1] for a in an_refs]
+    crossings = [cx[max(j for j in range(1, len(c)) if c[j] > 0.01)] for c in rs]
+    thr = float(np.median(crossings))
+    avg = average_contiguous_labels(label2)
+    anomaly = anomaly * (avg > 0.5)
+    anomaly = np.where((avg > 1.5) & (avg < 2.5), median_3mm(anomaly, vox), anomaly)
+    tissue = sum((np.asarray(t) > 0.5).astype(np.float32) for t in label2) > len(label2) / 2
+    anomaly = anomaly * tissue
+    return anomaly, valid, cx, cy, np.mean(rs, axis=0), thr, {"averaged_label": avg, "rough_brain": rough, "mean": r["mean"],
+                                                               "std": r["std"], "x_prime": r["x_prime"], "local_mu": r["local_mu"]}

@@ -12,7 +12,8 @@ unmodified (third-party modules that are absent here and not touched by these fu
 matplotlib, ... -- are replaced by inert stand-ins; NIfTI file access of the two stage-2 workers is redirected to an
 in-memory dict) and stores their outputs on seeded inputs in tests/golden/intree_v1.npz.
 
-usage: python tests/golden/make_golden_intree.py
+usage: python tests/golden/make_golden_intree.py                 -> intree_v1.npz
+       python tests/golden/make_golden_intree.py nll_analysis    -> nll_analysis_v1.npz (the whole nll_analysis, end to end)
 """
 import os
 import sys
@@ -180,5 +181,57 @@ def main():
     print("wrote intree_v1.npz:", len(conv), "arrays;", "stubbed:", ", ".join(stubbed))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "nll_analysis" not in sys.argv[1:]:
     main()
+
+
+def nll_analysis_fixture():
+    """Run the reference's nll_analysis (lesion_analysis.py:115-281) END TO END, unmodified, on seeded in-memory volumes:
+    its NIfTI readers / writers are redirected to a dict, the plot is a no-op, apply_otsu=False (skimage is absent).
+    -> tests/golden/nll_analysis_v1.npz"""
+    io, la, mt, ms, stubbed = import_reference()
+    rng = np.random.default_rng(23)
+    shape, k = (44, 52, 40), 6
+    g = np.stack(np.meshgrid(*[np.linspace(-1, 1, s) for s in shape], indexing="ij"))
+    r2 = (g ** 2).sum(0)
+    base = (100 + 25 * g[0] + 15 * np.cos(2 * g[1]) * g[2]).astype("float32")
+    store, brains, tissues, refs = {}, [], [], []
+    for i in range(k):
+        rad = 0.78 + 0.04 * rng.random()
+        brain = (r2 < rad).astype("float32")
+        # tissue labels 0..3 (background / cerebrum / cerebellum + brainstem / cortex), slightly different per reference
+        t = np.zeros(shape, "float32")
+        t[r2 < rad] = 3
+        t[r2 < rad - 0.12] = 1
+        t[(r2 < rad - 0.05) & (g[2] < -0.35 + 0.03 * rng.random()) & (g[1] < 0.1)] = 2
+        img = ((base * rng.uniform(0.85, 1.15) + rng.normal(0, 7, shape)) * brain).astype("float32")
+        store["r%d" % i], store["m%d" % i], store["y%d" % i] = img, brain, t
+        refs.append(img); brains.append(brain); tissues.append(t)
+    target = (base + rng.normal(0, 7, shape)).astype("float32")
+    target[14:18, 22:27, 20:24] += 70.0                              # lesion in the cerebrum
+    target[20:23, 12:15, 6:9] += 60.0                                # lesion in the cerebellum (median-filtered region)
+    target *= (r2 < 0.8)
+    store["x"] = target
+    vox = (1.0, 1.2, 1.1)
+    la.get_nifti_pixdim = lambda p: list(vox)
+    la.load_nifti_simple = lambda p: np.asarray(store[p]).astype("float32")
+    la.load_nifti = lambda p: (np.asarray(store[p]).astype("float32"), None)
+    la.save_nifti = lambda data, hdr, p: store.__setitem__("out:" + os.path.basename(p), np.asarray(data))
+    la.hist_plot = lambda *a, **kw: None
+    la.mkdir = lambda p: p
+    case = {"x": "x", "r": ["r%d" % i for i in range(k)], "m": ["m%d" % i for i in range(k)], "y": ["y%d" % i for i in range(k)]}
+    out = {"in_target": target, "in_refs": np.stack(refs), "in_label1": np.stack(brains), "in_label2": np.stack(tissues).astype(np.uint8),
+           "voxel_size": np.array(vox)}
+    for prior, tag in (("+", "pos"), (None, "none")):
+        an, valid, cx, cy, cr, thr = la.nll_analysis(case, apply_otsu=False, intensity_prior=prior, case_output_folder="o", debug=True)
+        out["anomaly_" + tag], out["valid_" + tag] = np.asarray(an, np.float32), np.asarray(valid, np.float32)
+        out["curve_x_" + tag], out["curve_y_" + tag], out["curve_r_" + tag] = cx, cy, cr
+        out["threshold_" + tag] = np.array(thr)
+        for name in ("normalized_input", "intensity_thr", "rough_brain", "local_mean", "mean_value", "std_value", "averaged_label"):
+            out[name + "_" + tag] = np.asarray(store["out:" + name + ".nii.gz"], np.float32)
+    np.savez_compressed(os.path.join(HERE, "nll_analysis_v1.npz"), **out)
+    print("wrote nll_analysis_v1.npz:", {k_: (v.shape if hasattr(v, "shape") else v) for k_, v in out.items() if k_.startswith(("thr", "curve_x"))})
+
+
+if __name__ == "__main__" and "nll_analysis" in sys.argv[1:]:
+    nll_analysis_fixture()

@@ -221,3 +221,27 @@ def test_full_size_volume_against_oracle(S):
     assert abs(inside.mean()) < 1e-5 and abs(inside.std() - 1.0) < 1e-5
     assert np.unique(z[brain < 0.5]).size == 1 and z[brain < 0.5][0] == np.float32(inside.min())
     assert (h(r["std"]) >= np.float32(0.03)).all() and (an32[valid < 0.5] == 0).all()
+
+
+@pytest.mark.parametrize("tag,prior", [("pos", "+"), ("none", None)])
+def test_whole_nll_analysis_matches_the_reference_run_end_to_end(S, tag, prior):
+    """tests/golden/nll_analysis_v1.npz holds what the reference's nll_analysis ITSELF returned and saved (run unmodified with
+    its NIfTI I/O redirected to memory, apply_otsu=False); stage1.nll_analysis_arrays is the device path for the same arrays."""
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "nll_analysis_v1.npz"))
+    an, valid, cx, cy, cr, thr, ex = S.nll_analysis_arrays(f["in_target"], list(f["in_refs"]), list(f["in_label1"]),
+                                                           [t.astype(np.float32) for t in f["in_label2"]], f["voxel_size"].tolist(),
+                                                           apply_otsu=False, intensity_prior=prior)
+    assert np.array_equal(h(valid), f["valid_" + tag]) and np.array_equal(h(ex["rough_brain"]), f["rough_brain_" + tag])
+    assert np.array_equal(h(ex["averaged_label"]), f["averaged_label_" + tag])
+    assert np.allclose(h(ex["normalized_input"]), f["normalized_input_" + tag], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(ex["local_mean"]), f["local_mean_" + tag], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(ex["mean"]), f["mean_value_" + tag], rtol=1e-5, atol=1e-5)
+    assert np.allclose(h(ex["std"]) * f["valid_" + tag], f["std_value_" + tag], rtol=1e-4, atol=1e-5)
+    assert np.allclose(h(an), f["anomaly_" + tag], rtol=1e-4, atol=2e-3)
+    # histogram curves: a voxel whose score sits within fp32 rounding of a bin edge may change bins, which moves a
+    # log10 count visibly only where counts are tiny -> all but a few of the 400 bins agree to 1e-2
+    assert np.allclose(cx, f["curve_x_" + tag], rtol=1e-6)
+    assert (np.abs(cy - f["curve_y_" + tag]) > 1e-2).sum() <= 4 and (np.abs(cr - f["curve_r_" + tag]) > 1e-2).sum() <= 4
+    assert abs(thr - float(f["threshold_" + tag])) <= 1.01 * (cx[1] - cx[0])
+    a = h(an)
+    assert a[20:23, 12:15, 6:9].max() > thr and a[14:18, 22:27, 20:24].max() > thr          # both planted lesions are found

@@ -109,3 +109,19 @@ def test_anomaly_pipeline(g):
     assert np.allclose(r["anomaly"], g["pipe_anomaly"], rtol=1e-4, atol=2e-3)
     an0 = I.nll(r["refs"][0], r["refs"], min_std=0.03, side="+") * g["in_valid"]
     assert np.allclose(an0, g["pipe_ref_anomaly0"], rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("tag,prior", [("pos", "+"), ("none", None)])
+def test_whole_nll_analysis_against_the_reference_run_end_to_end(tag, prior):
+    """tests/golden/nll_analysis_v1.npz = the reference's nll_analysis itself (NIfTI I/O redirected to memory)."""
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "nll_analysis_v1.npz"))
+    an, valid, cx, cy, cr, thr, ex = I.nll_analysis_arrays(f["in_target"], list(f["in_refs"]), list(f["in_label1"]),
+                                                           [t.astype(np.float32) for t in f["in_label2"]], f["voxel_size"].tolist(), prior)
+    assert np.array_equal(valid, f["valid_" + tag]) and np.array_equal(ex["rough_brain"], f["rough_brain_" + tag])
+    assert np.array_equal(ex["averaged_label"], f["averaged_label_" + tag])
+    assert np.allclose(ex["x_prime"], f["normalized_input_" + tag], rtol=1e-5, atol=1e-5)
+    assert np.allclose(ex["mean"], f["mean_value_" + tag], rtol=1e-5, atol=1e-5)
+    assert np.allclose(an, f["anomaly_" + tag], rtol=1e-4, atol=2e-3)
+    assert np.allclose(cx, f["curve_x_" + tag], rtol=1e-6) and np.allclose(cy, f["curve_y_" + tag], atol=1e-6)
+    assert np.allclose(cr, f["curve_r_" + tag], atol=1e-6) and thr == pytest.approx(float(f["threshold_" + tag]), rel=1e-6)
+    assert an[20:23, 12:15, 6:9].max() > thr and an[14:18, 22:27, 20:24].max() > thr      # both planted lesions are found
