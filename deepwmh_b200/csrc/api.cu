@@ -934,7 +934,7 @@ extern "C" int dwmh_remove_sparks(dwmh_ctx* c, const uint8_t* seg, int32_t X, in
   DW_TRY(grow(&c->ccl_sizes, &c->ccl_cap_s, (size_t)V));
   cudaStream_t st = (cudaStream_t)stream_;
   const int grid = c->num_sms * 8;
-  ccl_init_kernel<<<grid, 256, 0, st>>>(seg, c->ccl_labels, c->ccl_sizes, V);
+  ccl_init_kernel<<<grid, 256, 0, st>>>(seg, c->ccl_labels, c->ccl_sizes, V, Z);
   ccl_merge_kernel<<<grid, 256, 0, st>>>(c->ccl_labels, X, Y, Z);
   ccl_count_kernel<<<grid, 256, 0, st>>>(c->ccl_labels, c->ccl_sizes, V);
   ccl_filter_kernel<<<grid, 256, 0, st>>>(c->ccl_labels, c->ccl_sizes, out, min_volume, V);

@@ -465,16 +465,23 @@ __device__ __forceinline__ void cf_coords(int64_t v, const Dims& d, int (&c)[3])
 
 __global__ void __launch_bounds__(256) cf_erode_init_kernel(const float* __restrict__ mask, int* __restrict__ L, int* __restrict__ size,
                                                             Dims d, int ax, int64_t V) {
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
-    int c[3];
-    cf_coords(v, d, c);
-    bool keep = mask[v] != 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v0 = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); v0 < V; v0 += stride) {   // warp-uniform trip count
+    const int64_t v = v0 + (threadIdx.x & 31);
+    const bool in = v < V;
+    int c[3] = {0, 0, 0};
+    bool keep = false;
+    if (in) {
+      cf_coords(v, d, c);
+      keep = mask[v] != 0.f;
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
-      if (a != ax && keep)
-        keep = c[a] > 0 && c[a] + 1 < d.n[a] && mask[v - d.stride[a]] != 0.f && mask[v + d.stride[a]] != 0.f;
-    L[v] = keep ? (int)v : -1;
-    size[v] = 0;
+      for (int a = 0; a < 3; ++a)
+        if (a != ax && keep)
+          keep = c[a] > 0 && c[a] + 1 < d.n[a] && mask[v - d.stride[a]] != 0.f && mask[v + d.stride[a]] != 0.f;
+    }
+    // z-runs are components of the slice unless z is the slicing axis (then voxels along z belong to different slices)
+    const int l = ax != 2 ? dwmh::ccl_run_start(keep, in && c[2] == 0, v) : (keep ? (int)v : -1);
+    if (in) { L[v] = l; size[v] = 0; }
   }
 }
 
@@ -484,8 +491,11 @@ __global__ void __launch_bounds__(256) cf_merge_kernel(int* __restrict__ L, Dims
     int c[3];
     cf_coords(v, d, c);
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
-      if (a != ax && c[a] + 1 < d.n[a] && L[v + d.stride[a]] >= 0) dwmh::ccl_union(L, (int)v, (int)(v + d.stride[a]));
+    for (int a = 0; a < 3; ++a) {
+      if (a == ax || c[a] + 1 >= d.n[a] || L[v + d.stride[a]] < 0) continue;
+      if (a == 2 && ((v + 1) & 31) != 0) continue;                   // linked by the run initialisation
+      dwmh::ccl_union(L, (int)v, (int)(v + d.stride[a]));
+    }
   }
 }
 
