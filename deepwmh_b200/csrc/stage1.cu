@@ -144,35 +144,39 @@ struct GridGeom {
 constexpr int CS_SLAB = 5;          // x-planes per CTA
 __global__ void __launch_bounds__(256) s1_cell_sums_kernel(VolPtrs vols, const float* __restrict__ mask,
                                                            GridGeom q, int slabs, double* __restrict__ cells_all) {
-  extern __shared__ double zs[];    // [3][g2]
+  extern __shared__ double zs[];    // [3][min(Z, chunk)] per-z sums of the current z chunk
   const float* __restrict__ x = vols.p[blockIdx.y];
   double* cells = cells_all + (size_t)blockIdx.y * q.g[0] * q.g[1] * q.g[2] * 3;
   const int slab = blockIdx.x % slabs, cy = (blockIdx.x / slabs) % q.g[1], cx = blockIdx.x / (slabs * q.g[1]);
   const int x0 = cx * q.st[0] + slab * CS_SLAB, x1 = min(min(x0 + CS_SLAB, (cx + 1) * q.st[0]), q.X);
   const int y0 = cy * q.st[1], y1 = min(y0 + q.st[1], q.Y);
-  for (int i = threadIdx.x; i < 3 * q.g[2]; i += blockDim.x) zs[i] = 0.0;
-  __syncthreads();
-  for (int z = threadIdx.x; z < q.Z; z += 256) {
+  const int T = blockDim.x;
+  for (int zb = 0; zb < q.Z; zb += T) {
+    const int z = zb + threadIdx.x;
     double s = 0.0, ss = 0.0, cnt = 0.0;
-    for (int xi = x0; xi < x1; ++xi) {
-      const float* px = x + ((int64_t)xi * q.Y + y0) * q.Z + z;
-      const float* pm = mask ? mask + ((int64_t)xi * q.Y + y0) * q.Z + z : nullptr;
+    if (z < q.Z)
+      for (int xi = x0; xi < x1; ++xi) {
+        const float* px = x + ((int64_t)xi * q.Y + y0) * q.Z + z;
+        const float* pm = mask ? mask + ((int64_t)xi * q.Y + y0) * q.Z + z : nullptr;
 #pragma unroll 8
-      for (int yi = 0; yi < y1 - y0; ++yi) {
-        const float v = __ldg(px + (int64_t)yi * q.Z);
-        const bool m = !pm || __ldg(pm + (int64_t)yi * q.Z) > 0.5f;
-        if (m) { s += v; ss += (double)v * v; cnt += 1.0; }
+        for (int yi = 0; yi < y1 - y0; ++yi) {
+          const float v = __ldg(px + (int64_t)yi * q.Z);
+          const bool m = !pm || __ldg(pm + (int64_t)yi * q.Z) > 0.5f;
+          if (m) { s += v; ss += (double)v * v; cnt += 1.0; }
+        }
       }
+    zs[threadIdx.x] = s; zs[T + threadIdx.x] = ss; zs[2 * T + threadIdx.x] = cnt;
+    __syncthreads();
+    // fold the z coordinates of this chunk into their cells: one thread per (cell, quantity), a short sequential sum
+    const int c_lo = zb / q.st[2], c_hi = min((min(zb + T, q.Z) - 1) / q.st[2], q.g[2] - 1);
+    for (int i = threadIdx.x; i < 3 * (c_hi - c_lo + 1); i += T) {
+      const int cz = c_lo + i / 3, w = i % 3;
+      const int z_lo = max(cz * q.st[2], zb), z_hi = min(min((cz + 1) * q.st[2], zb + T), q.Z);
+      double acc = 0.0;
+      for (int zz = z_lo; zz < z_hi; ++zz) acc += zs[w * T + (zz - zb)];
+      if (acc != 0.0) atomicAdd(cells + ((size_t)(cx * q.g[1] + cy) * q.g[2] + cz) * 3 + w, acc);
     }
-    if (cnt > 0.0) {
-      const int cz = z / q.st[2];
-      atomicAdd(&zs[cz], s); atomicAdd(&zs[q.g[2] + cz], ss); atomicAdd(&zs[2 * q.g[2] + cz], cnt);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 3 * q.g[2]; i += blockDim.x) {
-    const int cz = i % q.g[2], w = i / q.g[2];
-    if (zs[i] != 0.0) atomicAdd(cells + ((size_t)(cx * q.g[1] + cy) * q.g[2] + cz) * 3 + w, zs[i]);
+    __syncthreads();
   }
 }
 
@@ -260,10 +264,15 @@ __global__ void __launch_bounds__(256) s1_align_kernel(float* __restrict__ x, co
 // the two coarse grids in fp64 -- the references' local-mean volumes are never materialised.
 __global__ void __launch_bounds__(256) s1_zoom_align_kernel(const double* __restrict__ mean_grids, size_t grid_stride, GridGeom q,
                                                             VolPtrs vols, float* __restrict__ mu_out) {
+  // dynamic smem: per-warp profiles [8][2][G2] doubles, then the z tables fz[Z] (double) and k0[Z] (int) shared by the CTA
   extern __shared__ double prof_all[];
+  const int G1 = q.g[1] + 2, G2 = q.g[2] + 2;
+  double* fz_t = prof_all + 16 * G2;
+  int* k0_t = reinterpret_cast<int*>(fz_t + q.Z);
+  for (int z = threadIdx.x; z < q.Z; z += 256) { int k0; double fz; zoom_coord(z, q.st[2], q.g[2], q.scale[2], k0, fz); fz_t[z] = fz; k0_t[z] = k0; }
+  __syncthreads();
   const int x = blockIdx.x, w = threadIdx.x >> 5, y = blockIdx.y * 8 + w, lane = threadIdx.x & 31, vol = blockIdx.z;
   if (y >= q.Y || (vol == 0 && !mu_out)) return;                     // whole warp
-  const int G1 = q.g[1] + 2, G2 = q.g[2] + 2;
   double* pt = prof_all + (size_t)w * 2 * G2;
   double* pr = pt + G2;
   int i0, j0; double fx, fy;
@@ -276,12 +285,20 @@ __global__ void __launch_bounds__(256) s1_zoom_align_kernel(const double* __rest
   __syncwarp();
   const int64_t row = ((int64_t)x * q.Y + y) * q.Z;
   float* xr = vols.p[vol];
-  for (int z = lane; z < q.Z; z += 32) {
-    int k0; double fz;
-    zoom_coord(z, q.st[2], q.g[2], q.scale[2], k0, fz);
-    const double mt = pt[k0] * (1 - fz) + pt[k0 + 1] * fz;
-    if (vol == 0) mu_out[row + z] = (float)mt;
-    else xr[row + z] = (float)(((double)xr[row + z] - (pr[k0] * (1 - fz) + pr[k0 + 1] * fz)) + mt);
+  for (int zb = 0; zb < q.Z; zb += 128) {                            // four loads in flight per lane
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int z = zb + j * 32 + lane; v[j] = (vol && z < q.Z) ? xr[row + z] : 0.f; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int z = zb + j * 32 + lane;
+      if (z >= q.Z) continue;
+      const int k0 = k0_t[z];
+      const double fz = fz_t[z];
+      const double mt = pt[k0] * (1 - fz) + pt[k0 + 1] * fz;
+      if (vol == 0) mu_out[row + z] = (float)mt;
+      else xr[row + z] = (float)(((double)v[j] - (pr[k0] * (1 - fz) + pr[k0 + 1] * fz)) + mt);
+    }
   }
 }
 
@@ -636,6 +653,7 @@ int geom(int X, int Y, int Z, const int32_t patch[3], GridGeom* q) {
   return 0;
 }
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+int cs_threads(int Z) { const int t = (Z + 31) & ~31; return t < 256 ? t : 256; }   // one thread per z, whole warps
 
 }  // namespace
 
@@ -714,7 +732,7 @@ extern "C" int dwmh_s1_mean_std_grid(int32_t device, const float* x, const float
   const int slabs = (q.st[0] + CS_SLAB - 1) / CS_SLAB;
   if (q.g[2] > 300) return fail("dwmh_s1_mean_std_grid: %d cells along z exceed the shared-memory tables (300)", q.g[2]);
   VolPtrs vols{}; vols.p[0] = const_cast<float*>(x);
-  s1_cell_sums_kernel<<<(unsigned)(q.g[0] * q.g[1] * slabs), 256, 3 * q.g[2] * sizeof(double), st>>>(vols, mask, q, slabs, cells);
+  s1_cell_sums_kernel<<<(unsigned)(q.g[0] * q.g[1] * slabs), cs_threads(Z), 3 * cs_threads(Z) * sizeof(double), st>>>(vols, mask, q, slabs, cells);
   s1_grid_stats_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, st>>>(cells, q, mask ? 1 : 0, mg, sg, 0);
   if ((Y + 7) / 8 > 65535) return fail("dwmh_s1_mean_std_grid: volume too large");
   s1_grid_zoom_kernel<<<dim3(X, (Y + 7) / 8), 256, 16 * (q.g[2] + 2) * sizeof(double), st>>>(mg, sg, q, mean_out, std_out);
@@ -753,9 +771,11 @@ extern "C" int dwmh_s1_local_mean_align(int32_t device, const float* target, flo
   double* sg = mg + (size_t)nvol * gstride;
   S1_CU(cudaMemsetAsync(workspace, 0, cells_bytes + 2 * (size_t)nvol * gstride * sizeof(double), st));
   const int slabs = (q.st[0] + CS_SLAB - 1) / CS_SLAB;
-  s1_cell_sums_kernel<<<dim3((unsigned)(q.g[0] * q.g[1] * slabs), nvol), 256, 3 * q.g[2] * sizeof(double), st>>>(vols, mask, q, slabs, cells);
+  s1_cell_sums_kernel<<<dim3((unsigned)(q.g[0] * q.g[1] * slabs), nvol), cs_threads(Z), 3 * cs_threads(Z) * sizeof(double), st>>>(vols, mask, q, slabs, cells);
   s1_grid_stats_kernel<<<dim3((unsigned)((ncell + 127) / 128), nvol), 128, 0, st>>>(cells, q, mask ? 1 : 0, mg, sg, gstride);
-  s1_zoom_align_kernel<<<dim3(X, (Y + 7) / 8, nvol), 256, 16 * (q.g[2] + 2) * sizeof(double), st>>>(mg, gstride, q, vols, target_local_mu_out);
+  const size_t za_smem = 16 * (size_t)(q.g[2] + 2) * sizeof(double) + (size_t)Z * (sizeof(double) + sizeof(int));
+  if (za_smem > 48 * 1024) return fail("dwmh_s1_local_mean_align: Z = %d exceeds the shared-memory z table", Z);
+  s1_zoom_align_kernel<<<dim3(X, (Y + 7) / 8, nvol), 256, za_smem, st>>>(mg, gstride, q, vols, target_local_mu_out);
   S1_CU(cudaGetLastError());
   return 0;
 }
