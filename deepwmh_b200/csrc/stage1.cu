@@ -419,14 +419,14 @@ __device__ __forceinline__ void minmax_ends(uint32_t (&v)[W]) {     // min of v[
   for (int i = S / 2; i < S - 1; ++i) { const uint32_t lo = min(v[i], v[S - 1]), hi = max(v[i], v[S - 1]); v[i] = lo; v[S - 1] = hi; }
 }
 template <int KY, int KZ, int N>
-__device__ __forceinline__ uint32_t window_key(const uint32_t* __restrict__ base, int e_ty_tz_unused, int ty, int tz, int e) {
+__device__ __forceinline__ uint32_t window_key(const uint32_t* __restrict__ base, int ty, int tz, int e) {
   return e < N ? base[((e / (KY * KZ)) * ty + (e / KZ) % KY) * tz + e % KZ] : 0xffffffffu;   // e >= N: the +inf pad of even windows
 }
 template <int S, int W, int NP, int N, int KY, int KZ>
 __device__ __forceinline__ void forget_step(uint32_t (&v)[W], const uint32_t* __restrict__ base, int ty, int tz) {
   if constexpr (S >= 3) {
     constexpr int e = NP - (S - 2);                                  // index of the window value added at this size
-    if constexpr (S < W) v[0] = window_key<KY, KZ, N>(base, 0, ty, tz, e);
+    if constexpr (S < W) v[0] = window_key<KY, KZ, N>(base, ty, tz, e);
     minmax_ends<S, W>(v);
     forget_step<S - 1, W, NP, N, KY, KZ>(v, base, ty, tz);
   }
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(256) s1_median_small_kernel(const float* __res
   const uint32_t* base = tile + (lx * ty + ly) * tz + lz;
   uint32_t v[W];
 #pragma unroll
-  for (int e = 0; e < W; ++e) v[e] = window_key<KY, KZ, N>(base, 0, ty, tz, e);
+  for (int e = 0; e < W; ++e) v[e] = window_key<KY, KZ, N>(base, ty, tz, e);
   forget_step<W, W, NP, N, KY, KZ>(v, base, ty, tz);                 // ends with the median of the last three in v[1]
   out[((int64_t)gx * Y + gy) * Z + gz] = key2f(v[1]);
 }
@@ -605,8 +605,7 @@ __global__ void __launch_bounds__(256) s1_label_vote_kernel(RefPtrs labels, int 
                                                             float* __restrict__ tissue_majority, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    unsigned long long votes = 0ull;                                 // 16 x 4-bit... K <= 32 needs 6 bits: two words of 8 x 8-bit counters
-    unsigned long long votes_hi = 0ull;
+    unsigned long long votes = 0ull, votes_hi = 0ull;                // 2 x 8 label ids, one 8-bit counter each (K <= 32)
     int tissue = 0;
     for (int k = 0; k < K; ++k) {
       const float t = __ldg(labels.p[k] + i);
