@@ -575,7 +575,11 @@ __global__ void __launch_bounds__(256) s1_histogram_kernel(const float* __restri
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     float v = x[i];
-    if (mask && !(mask[i] >= 0.5f)) { if (!fill_outside) continue; v = fill; }
+    if (mask) {                                                       // data[mask > 0.5]  vs  np.where(mask < 0.5, fill, data)
+      const float m = mask[i];
+      if (fill_outside) { if (m < 0.5f) v = fill; }
+      else if (!(m > 0.5f)) continue;
+    }
     const double d = (double)v;
     if (!(d >= first && d <= last)) continue;                         // outside the range (and NaN): not counted
     int b = (int)((d - first) * norm);
