@@ -53,6 +53,8 @@ SYMBOLS = {
     "dwmh_s1_mean_std_grid": (C.c_int, [C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _P, _P, _P, _P]),
     "dwmh_s1_align_local_mean": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int64, _P]),
     "dwmh_s1_group_nll": (C.c_int, [C.c_int32, _P, C.POINTER(_P), C.c_int32, C.c_double, C.c_int32, _P, _P, _P, _P, C.c_int64, _P]),
+    "dwmh_s1_group_nll_masked": (C.c_int, [C.c_int32, _P, C.POINTER(_P), C.POINTER(_P), C.c_int32, C.c_double, C.c_int32, _P, _P, _P, _P,
+                                           C.c_int64, _P]),
     "dwmh_s1_median_filter": (C.c_int, [C.c_int32, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _P]),
     "dwmh_s1_component_filtering_workspace": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]),
     "dwmh_s1_component_filtering": (C.c_int, [C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), _P, _P, _P]),

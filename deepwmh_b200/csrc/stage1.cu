@@ -362,6 +362,37 @@ __global__ void __launch_bounds__(256) s1_group_nll_kernel(const float* __restri
   }
 }
 
+// group_mean / group_std with per-reference masks (image_ops.py:197-231: masked values become NaN, np.nanmean / np.nanstd
+// over the rest; the Otsu branch of nll, lesion_analysis.py:87-92).  A voxel no reference covers has mu = sigma = NaN and,
+// after np.nan_to_num, anomaly 0.
+__global__ void __launch_bounds__(256) s1_group_nll_masked_kernel(const float* __restrict__ xp, RefPtrs refs, RefPtrs masks, NllParams q,
+                                                                  const float* __restrict__ mul_mask, float* __restrict__ anomaly,
+                                                                  float* __restrict__ mu_out, float* __restrict__ sigma_out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double r0 = 0.0, sd = 0.0, sdd = 0.0;
+    int cnt = 0;
+    for (int k = 0; k < q.K; ++k) {
+      if (__ldg(masks.p[k] + i) < 0.5f) continue;                    // np.where(mask < 0.5, nan, data)
+      const double r = (double)__ldg(refs.p[k] + i);
+      if (cnt == 0) r0 = r;
+      else { const double d = r - r0; sd += d; sdd += d * d; }
+      ++cnt;
+    }
+    float an, mu, sg;
+    if (cnt == 0) {
+      an = 0.f * (mul_mask ? mul_mask[i] : 1.f);
+      mu = sg = __int_as_float(0x7fc00000);
+    } else {
+      NllParams qq = q; qq.K = cnt;
+      nll_finish((double)xp[i], r0, sd, sdd, qq, mul_mask ? mul_mask[i] : 1.f, an, mu, sg);
+    }
+    if (anomaly) anomaly[i] = an;
+    if (mu_out) mu_out[i] = mu;
+    if (sigma_out) sigma_out[i] = sg;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // median filter, scipy.ndimage.median_filter(size=(kx,ky,kz), mode='constant', cval=0): window [i - k/2, i - k/2 + k)
 // per axis, rank (kx ky kz) / 2 of the ascending window.  One thread per voxel, CTA tile 2 x 4 x 32 (z fastest) staged
@@ -791,21 +822,43 @@ extern "C" int dwmh_s1_align_local_mean(int32_t device, float* x, const float* l
   return 0;
 }
 
-extern "C" int dwmh_s1_group_nll(int32_t device, const float* x_prime, const float* const* refs, int32_t k, double min_std, int32_t side,
-                                 const float* mul_mask, float* anomaly, float* mu_out, float* sigma_out, int64_t n, void* stream_) {
-  if (!x_prime || !refs) return fail("dwmh_s1_group_nll: null argument");
-  if (k <= 0 || k > S1_MAX_REFS) return fail("dwmh_s1_group_nll: k = %d reference images (1..%d supported)", k, S1_MAX_REFS);
-  if (side < -1 || side > 1) return fail("dwmh_s1_group_nll: side must be -1, 0 or +1");
-  RefPtrs rp{};
-  for (int i = 0; i < k; ++i) { if (!refs[i]) return fail("dwmh_s1_group_nll: refs[%d] is null", i); rp.p[i] = refs[i]; }
+static int group_nll_impl(const char* who, int32_t device, const float* x_prime, const float* const* refs, const float* const* masks, int32_t k,
+                          double min_std, int32_t side, const float* mul_mask, float* anomaly, float* mu_out, float* sigma_out, int64_t n,
+                          void* stream_) {
+  if (!x_prime || !refs) return fail("%s: null argument", who);
+  if (k <= 0 || k > S1_MAX_REFS) return fail("%s: k = %d reference images (1..%d supported)", who, k, S1_MAX_REFS);
+  if (side < -1 || side > 1) return fail("%s: side must be -1, 0 or +1", who);
+  RefPtrs rp{}, mp{};
+  for (int i = 0; i < k; ++i) {
+    if (!refs[i] || (masks && !masks[i])) return fail("%s: refs[%d] / masks[%d] is null", who, i, i);
+    rp.p[i] = refs[i];
+    if (masks) mp.p[i] = masks[i];
+  }
   S1_CU(cudaSetDevice(device));
-  uintptr_t al = (uintptr_t)x_prime | (uintptr_t)mul_mask | (uintptr_t)anomaly | (uintptr_t)mu_out | (uintptr_t)sigma_out;
-  for (int i = 0; i < k; ++i) al |= (uintptr_t)refs[i];
   const NllParams q{min_std, side, k};
-  if ((al & 15) == 0) s1_group_nll_kernel<true><<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x_prime, rp, q, mul_mask, anomaly, mu_out, sigma_out, n);
-  else s1_group_nll_kernel<false><<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x_prime, rp, q, mul_mask, anomaly, mu_out, sigma_out, n);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (masks) {
+    s1_group_nll_masked_kernel<<<grid_for(device), 256, 0, st>>>(x_prime, rp, mp, q, mul_mask, anomaly, mu_out, sigma_out, n);
+  } else {
+    uintptr_t al = (uintptr_t)x_prime | (uintptr_t)mul_mask | (uintptr_t)anomaly | (uintptr_t)mu_out | (uintptr_t)sigma_out;
+    for (int i = 0; i < k; ++i) al |= (uintptr_t)refs[i];
+    if ((al & 15) == 0) s1_group_nll_kernel<true><<<grid_for(device), 256, 0, st>>>(x_prime, rp, q, mul_mask, anomaly, mu_out, sigma_out, n);
+    else s1_group_nll_kernel<false><<<grid_for(device), 256, 0, st>>>(x_prime, rp, q, mul_mask, anomaly, mu_out, sigma_out, n);
+  }
   S1_CU(cudaGetLastError());
   return 0;
+}
+
+extern "C" int dwmh_s1_group_nll(int32_t device, const float* x_prime, const float* const* refs, int32_t k, double min_std, int32_t side,
+                                 const float* mul_mask, float* anomaly, float* mu_out, float* sigma_out, int64_t n, void* stream_) {
+  return group_nll_impl("dwmh_s1_group_nll", device, x_prime, refs, nullptr, k, min_std, side, mul_mask, anomaly, mu_out, sigma_out, n, stream_);
+}
+
+extern "C" int dwmh_s1_group_nll_masked(int32_t device, const float* x_prime, const float* const* refs, const float* const* ref_masks, int32_t k,
+                                        double min_std, int32_t side, const float* mul_mask, float* anomaly, float* mu_out, float* sigma_out,
+                                        int64_t n, void* stream_) {
+  if (!ref_masks) return fail("dwmh_s1_group_nll_masked: null argument");
+  return group_nll_impl("dwmh_s1_group_nll_masked", device, x_prime, refs, ref_masks, k, min_std, side, mul_mask, anomaly, mu_out, sigma_out, n, stream_);
 }
 
 extern "C" int dwmh_s1_median_filter(int32_t device, const float* in, float* out, int32_t X, int32_t Y, int32_t Z,

@@ -11,7 +11,7 @@ over the `dwmh_s1_*` entry points of include/deepwmh_b200.h.  Inputs may be nump
 results are fp32 CUDA tensors.  There is no CPU path: every function needs the library and a GPU.
 
 `threshold_otsu` restates skimage's published 256-bin algorithm (skimage is not vendored by the reference; that piece is
-`parity unpinned`).  Not built: `nll(use_mask=True)`, the histogram-curve threshold search and the NIfTI / plot output.
+`parity unpinned`).  Not built: the NIfTI / plot output of `nll_analysis`.
 """
 from __future__ import annotations
 
@@ -151,52 +151,59 @@ def _side(side: Optional[str]) -> int:
     return {None: 0, "+": 1, "-": -1}[side]
 
 
+def _group_nll(x: torch.Tensor, refs: Sequence[torch.Tensor], masks: Optional[Sequence[torch.Tensor]], min_std: float, side: int,
+               mul_mask: Optional[torch.Tensor], want_an: bool, want_stats: bool):
+    lib = _lib.load()
+    device = x.device.index
+    for r in list(refs) + list(masks or []):
+        if r.shape != x.shape:
+            raise ValueError("reference / mask shape %s != target shape %s" % (tuple(r.shape), tuple(x.shape)))
+    if masks is not None and len(masks) != len(refs):
+        raise ValueError("one mask per reference image is required")
+    an = torch.empty_like(x) if want_an else None
+    mu = torch.empty_like(x) if want_stats else None
+    sg = torch.empty_like(x) if want_stats else None
+    ptrs = (C.c_void_p * len(refs))(*[r.data_ptr() for r in refs])
+    with torch.cuda.device(x.device):
+        if masks is None:
+            _lib.check(lib.dwmh_s1_group_nll(device, _ptr(x), ptrs, len(refs), min_std, side, _ptr(mul_mask), _ptr(an), _ptr(mu), _ptr(sg),
+                                             x.numel(), _stream(device)))
+        else:
+            mptrs = (C.c_void_p * len(masks))(*[m.data_ptr() for m in masks])
+            _lib.check(lib.dwmh_s1_group_nll_masked(device, _ptr(x), ptrs, mptrs, len(refs), min_std, side, _ptr(mul_mask), _ptr(an),
+                                                    _ptr(mu), _ptr(sg), x.numel(), _stream(device)))
+    return an, mu, sg
+
+
 def nll(x_prime: Array, x_refs: Sequence[Array], min_std: Optional[float] = None, side: Optional[str] = None,
         return_all: bool = False, use_mask: bool = False, mul_mask: Optional[Array] = None, device: int = 0):
-    """lesion_analysis.py:84-113.  `mul_mask` (not in the reference signature) fuses the `anomaly * m_valid_score`
-    that follows every call (:175, :184)."""
-    if use_mask:
-        raise NotImplementedError("nll(use_mask=True) needs skimage's Otsu threshold, which is not built")
-    lib = _lib.load()
+    """lesion_analysis.py:84-113.  `use_mask`: every reference counts only where it exceeds its own Otsu threshold (:87-92).
+    `mul_mask` (not in the reference signature) fuses the `anomaly * m_valid_score` that follows every call (:175, :184)."""
     x = _dev(x_prime, device)
     refs = [_dev(r, device) for r in x_refs]
     if not refs:
         raise ValueError("nll: no reference images")
-    for r in refs:
-        if r.shape != x.shape:
-            raise ValueError("nll: reference shape %s != target shape %s" % (tuple(r.shape), tuple(x.shape)))
+    masks = [threshold_mask(r, threshold_otsu(r, device=device), device=device) for r in refs] if use_mask else None
     mm = _dev(mul_mask, device) if mul_mask is not None else None
-    an = torch.empty_like(x)
-    mu = torch.empty_like(x) if return_all else None
-    sg = torch.empty_like(x) if return_all else None
-    ptrs = (C.c_void_p * len(refs))(*[r.data_ptr() for r in refs])
-    with torch.cuda.device(x.device):
-        _lib.check(lib.dwmh_s1_group_nll(device, _ptr(x), ptrs, len(refs), -1.0 if min_std is None else float(min_std), _side(side),
-                                         _ptr(mm), _ptr(an), _ptr(mu), _ptr(sg), x.numel(), _stream(device)))
+    an, mu, sg = _group_nll(x, refs, masks, -1.0 if min_std is None else float(min_std), _side(side), mm, True, return_all)
     return (an, mu, sg) if return_all else an
 
 
-def group_mean(data_list: Sequence[Array], masks=None, device: int = 0) -> torch.Tensor:
-    """image_ops.py:216-231 (masks=None)."""
+def group_mean(data_list: Sequence[Array], masks: Optional[Sequence[Array]] = None, device: int = 0) -> torch.Tensor:
+    """image_ops.py:216-231 (NaN where every image is masked out)."""
     return _group(data_list, masks, device)[0]
 
 
-def group_std(data_list: Sequence[Array], masks=None, device: int = 0) -> torch.Tensor:
-    """image_ops.py:199-214 (masks=None): population std."""
+def group_std(data_list: Sequence[Array], masks: Optional[Sequence[Array]] = None, device: int = 0) -> torch.Tensor:
+    """image_ops.py:199-214: population std."""
     return _group(data_list, masks, device)[1]
 
 
 def _group(data_list, masks, device):
-    if masks is not None:
-        raise NotImplementedError("group_mean / group_std with masks (the Otsu branch of nll) is not built")
-    lib = _lib.load()
     refs = [_dev(r, device) for r in data_list]
-    mu, sg = torch.empty_like(refs[0]), torch.empty_like(refs[0])
-    ptrs = (C.c_void_p * len(refs))(*[r.data_ptr() for r in refs])
-    with torch.cuda.device(refs[0].device):
-        # min_std = 0: sigma is returned unmodified
-        _lib.check(lib.dwmh_s1_group_nll(device, _ptr(refs[0]), ptrs, len(refs), 0.0, 0, None, None, _ptr(mu), _ptr(sg),
-                                         refs[0].numel(), _stream(device)))
+    ms = [_dev(m, device) for m in masks] if masks is not None else None
+    # min_std = 0: sigma is returned unmodified
+    _, mu, sg = _group_nll(refs[0], refs, ms, 0.0, 0, None, False, True)
     return mu, sg
 
 

@@ -150,6 +150,12 @@ int dwmh_s1_align_local_mean(int32_t device, float* x_dev, const float* local_mu
  * anomaly / mu / sigma outputs may each be NULL. */
 int dwmh_s1_group_nll(int32_t device, const float* x_prime_dev, const float* const* refs, int32_t k, double min_std, int32_t side,
                       const float* mul_mask_dev, float* anomaly_dev, float* mu_out_dev, float* sigma_out_dev, int64_t n, void* stream);
+/* The same with one mask per reference (group_mean / group_std with masks, image_ops.py:197-231; the Otsu branch of nll,
+ * lesion_analysis.py:87-92): reference k counts at a voxel only where ref_masks[k] >= 0.5; a voxel no reference covers gets
+ * mu = sigma = NaN and anomaly 0 (np.nan_to_num). */
+int dwmh_s1_group_nll_masked(int32_t device, const float* x_prime_dev, const float* const* refs, const float* const* ref_masks, int32_t k,
+                             double min_std, int32_t side, const float* mul_mask_dev, float* anomaly_dev, float* mu_out_dev,
+                             float* sigma_out_dev, int64_t n, void* stream);
 /* scipy.ndimage.median_filter(size=kernel_size, mode='constant', cval=0) as used by median_3mm (image_ops.py:181-183,
  * 378-421; kernel-size rule on the host: deepwmh_b200/stage1.py).  Sizes 1..9 per axis, in != out.  Bit-exact. */
 int dwmh_s1_median_filter(int32_t device, const float* in_dev, float* out_dev, int32_t X, int32_t Y, int32_t Z,

@@ -11,6 +11,7 @@ statistics); inputs are numpy arrays [X, Y, Z].
 """
 from __future__ import annotations
 
+import warnings
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -85,22 +86,36 @@ def hard_dice_binary(y_true, y_pred):
     return 2 * np.sum(a * b) / (np.sum(a) + np.sum(b) + 0.000001)
 
 
-def group_mean(xs: Sequence[np.ndarray]):
-    """group_mean without masks, image_ops.py:216-231: voxelwise mean over the reference images (in the dtype of the
-    inputs, as np.nanmean of the stacked rows does: float32 volumes are averaged in float32)."""
-    return np.mean(np.stack([np.asarray(x) for x in xs]), axis=0)
+def _stack_masked(xs, masks):
+    rows = [np.asarray(x) for x in xs]
+    if masks is not None:
+        rows = [np.where(np.asarray(m) < 0.5, np.nan, x) for x, m in zip(rows, masks)]
+    return np.stack(rows)
 
 
-def group_std(xs: Sequence[np.ndarray]):
-    """group_std without masks, image_ops.py:199-214: voxelwise population std (dtype of the inputs)."""
-    return np.std(np.stack([np.asarray(x) for x in xs]), axis=0)
+def group_mean(xs: Sequence[np.ndarray], masks=None):
+    """group_mean, image_ops.py:216-231: voxelwise mean over the reference images (in the dtype of the inputs, as
+    np.nanmean of the stacked rows does: float32 volumes are averaged in float32); voxels with mask < 0.5 are left out
+    (NaN where no image remains)."""
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.nanmean(_stack_masked(xs, masks), axis=0)
+
+
+def group_std(xs: Sequence[np.ndarray], masks=None):
+    """group_std, image_ops.py:199-214: voxelwise population std (dtype of the inputs), masks as above."""
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return np.nanstd(_stack_masked(xs, masks), axis=0)
 
 
 def nll(x_prime, x_refs: List[np.ndarray], min_std: Optional[float] = None, side: Optional[str] = None,
-        return_all: bool = False):
-    """nll, deepwmh/analysis/lesion_analysis.py:84-113 (use_mask=False branch; Otsu masks need skimage)."""
+        return_all: bool = False, use_mask: bool = False):
+    """nll, deepwmh/analysis/lesion_analysis.py:84-113; use_mask: every reference contributes only where it exceeds its
+    own Otsu threshold (:87-92; threshold_otsu below is the unpinned restatement of skimage's)."""
     assert side in (None, "+", "-")
-    mu, sigma = group_mean(x_refs), group_std(x_refs)
+    masks = [np.where(x > threshold_otsu(x), 1, 0) for x in x_refs] if use_mask else None
+    mu, sigma = group_mean(x_refs, masks), group_std(x_refs, masks)
     sigma = sigma + 1e-6 if min_std is None else np.where(sigma < min_std, min_std, sigma)
     x = np.asarray(x_prime)
     with np.errstate(all="ignore"):

@@ -173,6 +173,21 @@ def main():
     out["cf_empty"] = io.component_filtering(np.zeros((6, 7, 5), "float32"), [1.0, 1.0, 1.0]).astype(np.float32)
     out["pipe_anomaly_cf"] = an * valid * io.component_filtering(valid, [1.0, 1.0, 1.0])      # lesion_analysis.py:175-176
 
+    # ---- group_mean / group_std with masks (image_ops.py:197-231) and the Otsu branch of nll (lesion_analysis.py:87-92).
+    # skimage is absent, so for nll(use_mask=True) the restated threshold_otsu (oracle/intree_oracle.py, unpinned) is
+    # injected into the reference module; everything else on that path is the reference's own code.
+    rng2 = np.random.default_rng(31)
+    gm = [(rng2.random(zt.shape) > 0.35).astype("float32") for _ in zr]
+    gm[0][5:9] = 0; gm[1][5:9] = 0; gm[2][5:9] = 0; gm[3][5:9] = 0; gm[4][5:9] = 0     # a slab no reference covers -> NaN
+    out["gmask"] = np.stack(gm)
+    out["group_mean_masked"] = io.group_mean(zr, masks=gm)
+    out["group_std_masked"] = io.group_std(zr, masks=gm)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import intree_oracle as I
+    la.threshold_otsu = I.threshold_otsu
+    an, mu, sg = la.nll(zt, zr, min_std=0.03, side="+", return_all=True, use_mask=True)
+    out["nll_usemask"], out["nll_usemask_mu"], out["nll_usemask_sigma"] = an, mu, sg
+
     conv = {}
     for k_, v in out.items():
         v = np.asarray(v)

@@ -61,8 +61,17 @@ def test_group_statistics_and_nll_match_reference_fixture(g, S):
     assert np.allclose(h(S.nll(zt, zr)), g["nll_eps"], rtol=1e-4, atol=1e-4)
     an_m = S.nll(zt, zr, min_std=0.03, side="+", mul_mask=g["in_valid"])
     assert np.allclose(h(an_m), g["nll_pos"] * g["in_valid"], rtol=1e-4, atol=1e-4)
-    with pytest.raises(NotImplementedError):
-        S.nll(zt, zr, use_mask=True)
+    # masks per reference (image_ops.py:197-231) and the Otsu branch (reference code + the restated threshold_otsu)
+    gm = list(g["gmask"])
+    assert np.allclose(h(S.group_mean(zr, gm)), g["group_mean_masked"], rtol=1e-6, atol=1e-6, equal_nan=True)
+    assert np.allclose(h(S.group_std(zr, gm)), g["group_std_masked"], rtol=1e-5, atol=1e-6, equal_nan=True)
+    assert np.isnan(h(S.group_mean(zr, gm))[5:9]).all()
+    an, mu, sg = S.nll(zt, zr, min_std=0.03, side="+", return_all=True, use_mask=True)
+    assert np.allclose(h(an), g["nll_usemask"], rtol=1e-4, atol=1e-4)
+    assert np.allclose(h(mu), g["nll_usemask_mu"], rtol=1e-6, atol=1e-6, equal_nan=True)
+    assert np.allclose(h(sg), g["nll_usemask_sigma"], rtol=1e-5, atol=1e-6, equal_nan=True)
+    with pytest.raises(ValueError):
+        S.group_mean(zr, gm[:2])
     with pytest.raises(AssertionError):
         S.nll(zt, zr, side="x")
     with pytest.raises(Exception):

@@ -57,8 +57,4 @@ def test_unsupported_branches_raise_without_a_gpu():
     with pytest.raises(NotImplementedError):
         S.mean_std_grid(z, [2, 2, 2], order=3)
     with pytest.raises(NotImplementedError):
-        S.nll(z, [z], use_mask=True)
-    with pytest.raises(NotImplementedError):
-        S.group_mean([z], masks=[z])
-    with pytest.raises(NotImplementedError):
         S.component_filtering(z, [1, 1, 1], return_type="int")

@@ -69,6 +69,17 @@ def test_group_statistics_and_nll(g):
     assert (g["nll_pos"] != g["nll_none"]).any() and (g["nll_sigma"] >= np.float32(0.03)).all()
 
 
+def test_masked_group_statistics_and_otsu_branch_of_nll(g):
+    zt, zr, gm = g["z_target"], list(g["z_refs"]), list(g["gmask"])
+    assert np.allclose(I.group_mean(zr, gm), g["group_mean_masked"], equal_nan=True, **F32)
+    assert np.allclose(I.group_std(zr, gm), g["group_std_masked"], equal_nan=True, **F32)
+    assert np.isnan(g["group_mean_masked"][5:9]).all()
+    assert np.array_equal(np.isnan(g["group_mean_masked"]), (np.stack(gm) < 0.5).all(axis=0))     # NaN exactly where nothing is left
+    an, mu, sg = I.nll(zt, zr, min_std=0.03, side="+", return_all=True, use_mask=True)     # reference code + restated Otsu
+    assert np.allclose(an, g["nll_usemask"], **F32) and np.allclose(mu, g["nll_usemask_mu"], equal_nan=True, **F32)
+    assert np.allclose(sg, g["nll_usemask_sigma"], equal_nan=True, **F32)
+
+
 @pytest.mark.parametrize("tag", ["p12", "p50", "podd", "nomask"])
 def test_mean_std_grid(g, tag):
     if tag == "nomask":
