@@ -259,20 +259,22 @@ __global__ void __launch_bounds__(256) s1_align_kernel(float* __restrict__ x, co
     x[i] = (float)(((double)x[i] - (double)mu_i[i]) + (double)mu_p[i]);
 }
 
-// lesion_analysis.py:163-169 in one launch: blockIdx.z = 0 is the target (its zoomed local mean is written to mu_out,
-// if given), blockIdx.z >= 1 a reference, aligned in place: x_i = (x_i - zoom(grid_i)) + zoom(grid_target), evaluated from
+// lesion_analysis.py:163-169 in one launch: volume 0 is the target (its zoomed local mean is written to mu_out,
+// if given), volumes >= 1 the references, aligned in place: x_i = (x_i - zoom(grid_i)) + zoom(grid_target), evaluated from
 // the two coarse grids in fp64 -- the references' local-mean volumes are never materialised.
 __global__ void __launch_bounds__(256) s1_zoom_align_kernel(const double* __restrict__ mean_grids, size_t grid_stride, GridGeom q,
-                                                            VolPtrs vols, float* __restrict__ mu_out) {
-  // dynamic smem: per-warp profiles [8][2][G2] doubles, then the z tables fz[Z] (double) and k0[Z] (int) shared by the CTA
+                                                            VolPtrs vols, int nvol, float* __restrict__ mu_out) {
+  // dynamic smem: per-warp profiles [8][2][G2] doubles, then the z tables fz[Z] (double) and k0[Z] (int) shared by the CTA.
+  // One warp per (x, y) row; the row's coordinates, corner weights and target profile are set up once and serve the
+  // target and all k references (the volume loop is inside).
   extern __shared__ double prof_all[];
   const int G1 = q.g[1] + 2, G2 = q.g[2] + 2;
   double* fz_t = prof_all + 16 * G2;
   int* k0_t = reinterpret_cast<int*>(fz_t + q.Z);
   for (int z = threadIdx.x; z < q.Z; z += 256) { int k0; double fz; zoom_coord(z, q.st[2], q.g[2], q.scale[2], k0, fz); fz_t[z] = fz; k0_t[z] = k0; }
   __syncthreads();
-  const int x = blockIdx.x, w = threadIdx.x >> 5, y = blockIdx.y * 8 + w, lane = threadIdx.x & 31, vol = blockIdx.z;
-  if (y >= q.Y || (vol == 0 && !mu_out)) return;                     // whole warp
+  const int x = blockIdx.x, w = threadIdx.x >> 5, y = blockIdx.y * 8 + w, lane = threadIdx.x & 31;
+  if (y >= q.Y) return;                                              // whole warp
   double* pt = prof_all + (size_t)w * 2 * G2;
   double* pr = pt + G2;
   int i0, j0; double fx, fy;
@@ -281,24 +283,29 @@ __global__ void __launch_bounds__(256) s1_zoom_align_kernel(const double* __rest
   const size_t o4[4] = {((size_t)i0 * G1 + j0) * G2, ((size_t)i0 * G1 + j0 + 1) * G2, ((size_t)(i0 + 1) * G1 + j0) * G2,
                         ((size_t)(i0 + 1) * G1 + j0 + 1) * G2};
   row_profile(mean_grids, o4, wxy, G2, lane, pt);                    // target grid
-  if (vol) row_profile(mean_grids + (size_t)vol * grid_stride, o4, wxy, G2, lane, pr);
   __syncwarp();
   const int64_t row = ((int64_t)x * q.Y + y) * q.Z;
-  float* xr = vols.p[vol];
-  for (int zb = 0; zb < q.Z; zb += 128) {                            // four loads in flight per lane
-    float v[4];
+  if (mu_out)
+    for (int z = lane; z < q.Z; z += 32) { const int k0 = k0_t[z]; const double fz = fz_t[z]; mu_out[row + z] = (float)(pt[k0] * (1 - fz) + pt[k0 + 1] * fz); }
+  for (int vol = 1; vol < nvol; ++vol) {
+    row_profile(mean_grids + (size_t)vol * grid_stride, o4, wxy, G2, lane, pr);
+    __syncwarp();
+    float* xr = vols.p[vol];
+    for (int zb = 0; zb < q.Z; zb += 128) {                          // four loads in flight per lane
+      float v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { const int z = zb + j * 32 + lane; v[j] = (vol && z < q.Z) ? xr[row + z] : 0.f; }
+      for (int j = 0; j < 4; ++j) { const int z = zb + j * 32 + lane; v[j] = z < q.Z ? xr[row + z] : 0.f; }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int z = zb + j * 32 + lane;
-      if (z >= q.Z) continue;
-      const int k0 = k0_t[z];
-      const double fz = fz_t[z];
-      const double mt = pt[k0] * (1 - fz) + pt[k0 + 1] * fz;
-      if (vol == 0) mu_out[row + z] = (float)mt;
-      else xr[row + z] = (float)(((double)v[j] - (pr[k0] * (1 - fz) + pr[k0 + 1] * fz)) + mt);
+      for (int j = 0; j < 4; ++j) {
+        const int z = zb + j * 32 + lane;
+        if (z >= q.Z) continue;
+        const int k0 = k0_t[z];
+        const double fz = fz_t[z];
+        const double mt = pt[k0] * (1 - fz) + pt[k0 + 1] * fz;
+        xr[row + z] = (float)(((double)v[j] - (pr[k0] * (1 - fz) + pr[k0 + 1] * fz)) + mt);
+      }
     }
+    __syncwarp();                                                    // pr is rewritten for the next volume
   }
 }
 
@@ -809,7 +816,7 @@ extern "C" int dwmh_s1_local_mean_align(int32_t device, const float* target, flo
   s1_grid_stats_kernel<<<dim3((unsigned)((ncell + 127) / 128), nvol), 128, 0, st>>>(cells, q, mask ? 1 : 0, mg, sg, gstride);
   const size_t za_smem = 16 * (size_t)(q.g[2] + 2) * sizeof(double) + (size_t)Z * (sizeof(double) + sizeof(int));
   if (za_smem > 48 * 1024) return fail("dwmh_s1_local_mean_align: Z = %d exceeds the shared-memory z table", Z);
-  s1_zoom_align_kernel<<<dim3(X, (Y + 7) / 8, nvol), 256, za_smem, st>>>(mg, gstride, q, vols, target_local_mu_out);
+  s1_zoom_align_kernel<<<dim3(X, (Y + 7) / 8), 256, za_smem, st>>>(mg, gstride, q, vols, nvol, target_local_mu_out);
   S1_CU(cudaGetLastError());
   return 0;
 }
