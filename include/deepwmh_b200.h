@@ -117,6 +117,7 @@ int dwmh_remove_sparks(dwmh_ctx* ctx, const uint8_t* seg_dev, int32_t X, int32_t
 /* --- stage-1 NLL anomaly map (deepwmh/analysis/lesion_analysis.py:84-176) ---------------------------
  * Context-free (no network involved): `device` is the CUDA ordinal; every buffer is a caller-owned device pointer,
  * volumes fp32 [X][Y][Z], masks fp32 with the reference's `> 0.5` convention.  fp64 arithmetic per voxel, fp32 storage.
+ * Every call makes `device` the calling thread's current CUDA device (cudaSetDevice) and enqueues on `stream`.
  *
  * dwmh_s1_zscore: z_score (deepwmh/analysis/image_ops.py:172-179, masked_mean/std :13-21) in place:
  *   x = (x - mean_mask) / max(std_mask, 1e-5) for ALL voxels (mask NULL = statistics over everything).
