@@ -162,7 +162,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import deepwmh_b200
-    import oracle as O          # synthetic inputs + random-init weights + the cpu_baseline leg only
+    from deepwmh_b200 import workload as W      # synthetic volume + random-init weights (product side; oracle/ is only the cpu_baseline leg)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -174,15 +174,13 @@ def run_b200(args):
     pk = peaks()
 
     plans = deepwmh_b200.benchmark_plans()
-    net = O.build_benchmark_network(0)
     tr = deepwmh_b200.nnUNetTrainerV2(plans, device=local, act_dtype=args.dtype, max_batch=args.max_batch)
-    tr.load_checkpoint_ram({"state_dict": net.state_dict()}, False)
+    tr.load_checkpoint_ram({"state_dict": W.random_init_state_dict(plans, 0)}, False)
     n = tr.network
-    flops_fwd = O.forward_flops(O.benchmark_plans())
-    del net
+    flops_fwd = W.forward_flops(plans)
 
     # per-rank subject (cohort sharding: rank r owns subjects r, r+world, ...)
-    raws = [O.synthetic_flair(SHAPE, seed=rank + world * i)[0] for i in range(2)]
+    raws = [W.synthetic_flair(SHAPE, seed=rank + world * i)[0] for i in range(2)]
     raw_dev = [torch.from_numpy(r).to(dev) for r in raws]
     pinned = [torch.from_numpy(r).pin_memory() for r in raws]
     X, Y, Z = SHAPE
