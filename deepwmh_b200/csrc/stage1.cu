@@ -1,13 +1,17 @@
-// the stage-1 NLL anomaly map of deepwmh/analysis/lesion_analysis.py:84-176 on the device.
+// nll_analysis of deepwmh/analysis/lesion_analysis.py:115-281 (the stage-1 NLL anomaly map) on the device.
 // Voxel-parallel, HBM-bound kernels; fp32 storage, fp64 per-voxel arithmetic (the reference works in float64 once a
 // volume has been z-scored).  Context-free entry points (no network involved): `device` + caller-owned buffers.
 //
-//   dwmh_s1_zscore            z_score (image_ops.py:172-179) [+ tissue-min fill, lesion_analysis.py:150-151,160-161]
-//   dwmh_s1_mean_std_grid     mean_std_grid, order 1 (image_ops.py:56-170)
-//   dwmh_s1_align_local_mean  x_i - x_i_local_mu + x_prime_local_mu (lesion_analysis.py:166-169)
-//   dwmh_s1_group_nll         group_mean / group_std / nll (image_ops.py:197-231, lesion_analysis.py:84-113)
-//   dwmh_s1_median_filter     median_filter(mode='constant', cval=0) behind median_3mm (image_ops.py:181-183,378-421)
-//   dwmh_s1_component_filtering  component_filtering (image_ops.py:253-306)
+//   dwmh_s1_zscore[_batch]        z_score (image_ops.py:172-179) [+ tissue-min fill, lesion_analysis.py:150-151,160-161]
+//   dwmh_s1_mean_std_grid         mean_std_grid, order 1 (image_ops.py:56-170)
+//   dwmh_s1_local_mean_align      local means of a whole case + x_i - x_i_local_mu + x_prime_local_mu (lesion_analysis.py:163-169)
+//   dwmh_s1_align_local_mean      the alignment alone, from materialised local means
+//   dwmh_s1_group_nll[_masked]    group_mean / group_std / nll (image_ops.py:197-231, lesion_analysis.py:84-113)
+//   dwmh_s1_median_filter         median_filter(mode='constant', cval=0) behind median_3mm (image_ops.py:181-183,378-421)
+//   dwmh_s1_component_filtering   component_filtering (image_ops.py:253-306)
+//   dwmh_s1_minmax / _histogram / _threshold_mask   Otsu mask (lesion_analysis.py:142-148) and hist_curve (:40-50)
+//   dwmh_s1_masked_sums           bin width of histogram_analysis (:52-82)
+//   dwmh_s1_label_vote / _apply_priors   average_contiguous_labels (image_ops.py:23-38) and the tissue priors (:213-243)
 #include "../../include/deepwmh_b200.h"
 
 #include <cstdarg>
