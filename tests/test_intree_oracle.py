@@ -57,6 +57,16 @@ def test_hard_dice(g):
     assert I.hard_dice_binary(g["dice_in"][0], g["dice_in"][1]) == pytest.approx(ref, rel=1e-7)   # fp32 sums in the reference
 
 
+def test_the_parity_gates_own_helpers_are_pinned_too(g):
+    """oracle/nnunet_oracle.py: the Dice the BASELINE gate is quoted in and the in-tree z_score sibling, against the reference's output."""
+    import oracle as O
+    names = g["dice_names"].tolist()
+    ref = g["dice_vals"][names.index("hard_dice_binary")]
+    assert O.hard_dice_binary(g["dice_in"][0], g["dice_in"][1]) == pytest.approx(ref, rel=1e-7)
+    assert np.allclose(O.zscore_deepwmh(g["in_target"], g["in_brain"]), g["zscore_masked"], rtol=1e-5, atol=1e-5)
+    assert np.allclose(O.zscore_deepwmh(g["in_target"]), g["zscore_plain"], rtol=1e-5, atol=1e-5)
+
+
 def test_group_statistics_and_nll(g):
     zt, zr = g["z_target"], list(g["z_refs"])
     assert np.allclose(I.group_mean(zr), g["group_mean"], **F32)
