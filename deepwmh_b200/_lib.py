@@ -18,7 +18,7 @@ class NetDesc(C.Structure):
         ("max_num_features", C.c_int32), ("num_pool", C.c_int32), ("patch_size", C.c_int32 * 3),
         ("pool_op_kernel_sizes", (C.c_int32 * 3) * DWMH_MAX_POOL),
         ("conv_kernel_sizes", (C.c_int32 * 3) * (DWMH_MAX_POOL + 1)),
-        ("act_dtype", C.c_int32), ("max_batch", C.c_int32), ("lanes", C.c_int32),
+        ("act_dtype", C.c_int32), ("max_batch", C.c_int32), ("struct_size", C.c_int32),
     ]
 
 

@@ -34,6 +34,18 @@ static int fail(const char* fmt, ...) {
   return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 #define DW_TRY(expr) do { int r__ = (expr); if (r__) return r__; } while (0)
 
+// Entry points run on the context's device and leave the caller's current device as they found it.
+struct DevGuard {
+  int prev = -1; bool ok = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    if (prev == dev) prev = -1;
+  }
+  ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define DEV_GUARD(dev) DevGuard dev_guard__(dev); if (!dev_guard__.ok) return fail("cudaSetDevice(%d) failed", (int)(dev))
+
 extern "C" const char* dwmh_last_error(void) { return g_err.c_str(); }
 extern "C" void dwmh_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }   // for the other translation units (stage1.cu)
 extern "C" int dwmh_version(void) { return 100; }
@@ -65,7 +77,8 @@ struct Layer {
   int s2d_s[3] = {1, 1, 1};
   float* w_dev = nullptr;           // generic packing
   float* gamma_dev = nullptr; float* beta_dev = nullptr;
-  double* sums = nullptr;           // into the stats arena
+  double* sums = nullptr;           // into the stats arena: [maxN][cout][2] fp64
+  bool stats_mean_var = false;      // sums hold {mean, variance} (tcgen05 path) instead of {sum, sum of squares}
   TcLayer tc;                       // tcgen05 packing / tensor maps (valid iff tc.enabled)
   int64_t vin() const { return (int64_t)in_sp[0] * in_sp[1] * in_sp[2]; }
   int64_t vout() const { return (int64_t)out_sp[0] * out_sp[1] * out_sp[2]; }
@@ -73,18 +86,6 @@ struct Layer {
     if (kind == L_TCONV) return 2.0 * vout() * c0 * cout;
     return 2.0 * vout() * (double)(k[0] * k[1] * k[2]) * (c0 + c1) * cout;
   }
-};
-
-// One independent forward pipeline: its own activation buffers, statistics, probabilities, tensor maps and
-// stream.  HBM-bound kernels (norm, first conv, head) of one lane overlap with tensor-bound kernels of another.
-struct LaneLayer { void* out = nullptr; void* raw = nullptr; void* s2d = nullptr; double* sums = nullptr; CUtensorMap tm0, tm1; };
-struct Lane {
-  std::vector<LaneLayer> ll;
-  double* stats_arena = nullptr; float* probs = nullptr;
-  cudaStream_t stream = nullptr;      // tensor-core kernels (low priority)
-  cudaStream_t stream_aux = nullptr;  // HBM / CUDA-core kernels (high priority): slot in beside another lane's tcgen05 CTAs
-  std::vector<cudaEvent_t> hop; int hop_i = 0;
-  cudaEvent_t fwd_done = nullptr, agg_done = nullptr; bool agg_pending = false;
 };
 
 struct dwmh_ctx {
@@ -101,9 +102,10 @@ struct dwmh_ctx {
   bool force_generic = false;
   int raw32_max_edge = 64;
   // workspaces
-  double* stats_arena = nullptr; size_t stats_bytes = 0;   // views of the active lane
+  double* stats_arena = nullptr; size_t stats_bytes = 0;
+  StatPartial* stat_partials = nullptr; size_t stat_partials_cap = 0;   // per-CTA Welford partials of the layer in flight
   float* probs = nullptr;            // [maxN][2][P]
-  std::vector<Lane> lanes; int nlanes = 1; int active_lane = -1; cudaEvent_t ev_start = nullptr; bool split_streams = false;
+  bool buffers_ready = false;
   float* gauss_dev = nullptr; std::vector<float> gauss_host; bool gauss_custom = false;
   SampleMeta* metas_dev = nullptr; size_t metas_cap = 0;
   double* zs_acc = nullptr;
@@ -195,7 +197,10 @@ extern "C" int dwmh_create(dwmh_ctx** out, int device, const dwmh_net_desc* desc
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("dwmh_create: no CUDA device visible (this library has no CPU fallback)");
   if (device < 0 || device >= ndev) return fail("dwmh_create: device %d out of range (%d devices)", device, ndev);
-  CU_TRY(cudaSetDevice(device));
+  if (desc->struct_size != (int32_t)sizeof(dwmh_net_desc))
+    return fail("dwmh_create: dwmh_net_desc.struct_size is %d, this library expects %d (set it to sizeof(dwmh_net_desc); "
+                "a stale binding of the struct would otherwise be read past its end)", desc->struct_size, (int)sizeof(dwmh_net_desc));
+  DEV_GUARD(device);
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail("dwmh_create: device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major, prop.minor);
@@ -206,9 +211,6 @@ extern "C" int dwmh_create(dwmh_ctx** out, int device, const dwmh_net_desc* desc
   c->device = device; c->d = *desc; c->bf16 = desc->act_dtype == 1; c->num_sms = prop.multiProcessorCount;
   c->max_batch = desc->max_batch > 0 ? desc->max_batch : 8;
   if (const char* e = getenv("DWMH_RAW32_MAX_EDGE")) c->raw32_max_edge = atoi(e);
-  c->nlanes = desc->lanes > 0 ? desc->lanes : 1;
-  if (const char* e = getenv("DWMH_LANES")) c->nlanes = std::max(1, atoi(e));
-  if (const char* e = getenv("DWMH_SPLIT_STREAMS")) c->split_streams = atoi(e) != 0;
   if (build_plan(c)) { delete c; return 1; }
   for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev[i]);
   *out = c;
@@ -219,19 +221,14 @@ static void free_dev(void* p) { if (p) cudaFree(p); }
 
 extern "C" int dwmh_destroy(dwmh_ctx* c) {
   if (!c) return 0;
-  cudaSetDevice(c->device);
+  DevGuard dg(c->device);
   cudaDeviceSynchronize();
-  for (auto& ln : c->lanes) {
-    for (auto& b : ln.ll) { if (b.raw != b.out) free_dev(b.raw); free_dev(b.out); free_dev(b.s2d); }
-    free_dev(ln.stats_arena); free_dev(ln.probs);
-    if (ln.stream) cudaStreamDestroy(ln.stream);
-    if (ln.stream_aux) cudaStreamDestroy(ln.stream_aux);
-    for (auto e : ln.hop) cudaEventDestroy(e);
-    if (ln.fwd_done) cudaEventDestroy(ln.fwd_done);
-    if (ln.agg_done) cudaEventDestroy(ln.agg_done);
+  for (auto& L : c->layers) {
+    if (L.raw != L.out) free_dev(L.raw);
+    free_dev(L.out); free_dev(L.s2d);
+    free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc);
   }
-  if (c->ev_start) cudaEventDestroy(c->ev_start);
-  for (auto& L : c->layers) { free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc); }
+  free_dev(c->stats_arena); free_dev(c->probs); free_dev(c->stat_partials);
   free_dev(c->w_head_dev); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
   free_dev(c->hv_vol); free_dev(c->hv_pad); free_dev(c->hv_agg); free_dev(c->hv_wgt); free_dev(c->hv_seg);
   free_dev(c->ccl_labels); free_dev(c->ccl_sizes);
@@ -313,7 +310,7 @@ static int upload(V** dst, const std::vector<V>& src) {
 
 extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
   if (!c) return fail("null ctx");
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   if (!c->have_head) return fail("missing weight seg_outputs.%d.weight", c->d.num_pool - 1);
   for (auto& L : c->layers) {
     if (!L.have_w) return fail("missing weight for %s", L.name.c_str());
@@ -356,76 +353,61 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     if (L.kind == L_CONV && strided && L.k[0] == 3 && L.k[1] == 3 && L.k[2] == 3 && L.c0 % 16 == 0 && L.c1 == 0 && L.cout % 16 == 0)
       for (int a_ = 0; a_ < 3; ++a_) c->layers[L.in0].s2d_s[a_] = L.s[a_];
   }
-  // ---- per lane: activation buffers, statistics, probabilities ----
+  // ---- activation buffers, statistics, probabilities (allocated once per context) ----
   size_t stat_doubles = 0;
   for (auto& L : c->layers) if (L.has_norm) stat_doubles += (size_t)maxN * L.cout * 2;
   c->stats_bytes = stat_doubles * sizeof(double);
-  if (c->lanes.empty()) {
-    c->lanes.resize(c->nlanes);
-    CU_TRY(cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming));
-    for (auto& ln : c->lanes) {
-      ln.ll.resize(nL);
-      int prio_lo = 0, prio_hi = 0;
-      CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-      CU_TRY(cudaStreamCreateWithPriority(&ln.stream, cudaStreamNonBlocking, prio_lo));
-      CU_TRY(cudaStreamCreateWithPriority(&ln.stream_aux, cudaStreamNonBlocking, prio_hi));
-      ln.hop.resize(64);
-      for (auto& e : ln.hop) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      CU_TRY(cudaEventCreateWithFlags(&ln.fwd_done, cudaEventDisableTiming));
-      CU_TRY(cudaEventCreateWithFlags(&ln.agg_done, cudaEventDisableTiming));
-      CU_TRY(cudaMalloc((void**)&ln.stats_arena, c->stats_bytes));
-      CU_TRY(cudaMalloc((void**)&ln.probs, (size_t)maxN * 2 * c->P() * sizeof(float)));
-      size_t off = 0;
-      for (int i = 0; i < nL; ++i) {
-        Layer& L = c->layers[i];
-        LaneLayer& b = ln.ll[i];
-        if (L.has_norm) { b.sums = ln.stats_arena + off; off += (size_t)maxN * L.cout * 2; }
-        CU_TRY(cudaMalloc(&b.out, (size_t)maxN * L.cout * L.vout() * c->elt));
-        if (L.raw32) CU_TRY(cudaMalloc(&b.raw, (size_t)maxN * L.cout * L.vout() * 4)); else b.raw = b.out;
-        const bool need_s2d = L.s2d_s[0] * L.s2d_s[1] * L.s2d_s[2] > 1;
-        if (need_s2d) CU_TRY(cudaMalloc(&b.s2d, (size_t)maxN * L.cout * L.vout() * c->elt));
-      }
-    }
-  }
-  // ---- tcgen05 packing (shared) + tensor maps (per lane) ----
-  for (int li = 0; li < (int)c->lanes.size(); ++li) {
-    Lane& ln = c->lanes[li];
+  if (!c->buffers_ready) {
+    CU_TRY(cudaMalloc((void**)&c->stats_arena, c->stats_bytes));
+    CU_TRY(cudaMalloc((void**)&c->probs, (size_t)maxN * 2 * c->P() * sizeof(float)));
+    size_t off = 0;
     for (int i = 0; i < nL; ++i) {
       Layer& L = c->layers[i];
-      LaneLayer& b = ln.ll[i];
-      if (L.kind == L_FIRST) {
-        if (li == 0) {
-          tc_free(L.tc);
-          static int allow_first = -1;
-          if (allow_first < 0) { const char* e = getenv("DWMH_TC_FIRST"); allow_first = e ? atoi(e) : 1; }
-          std::string why;
-          if (allow_first && L.k[0] == 3 && L.k[1] == 3 && L.k[2] == 3 && L.c0 == 1) {
-            std::vector<float> w27((size_t)27 * L.cout);
-            for (int co = 0; co < L.cout; ++co) for (int t = 0; t < 27; ++t) w27[(size_t)t * L.cout + co] = L.w[(size_t)co * 27 + t];
-            if (tc_prepare_first(L.tc, w27, L.cout, L.out_sp, c->bf16, b.raw, &why))
-              if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
-          }
-        }
-        b.tm0 = L.tc.tm0; b.tm1 = L.tc.tm1;
-        continue;
-      }
-      const void* in0 = ln.ll[L.in0].out;
-      const void* in1 = L.in1 >= 0 ? ln.ll[L.in1].out : nullptr;
-      const bool strided = L.kind == L_CONV && (L.s[0] != 1 || L.s[1] != 1 || L.s[2] != 1);
-      if (strided && ln.ll[L.in0].s2d) in0 = ln.ll[L.in0].s2d;
-      std::string why;
-      if (li == 0) {
-        tc_free(L.tc);
-        if (L.kind == L_TCONV) {
-          if (tc_prepare_tconv(L.tc, L.w, L.c0, L.cout, L.s, L.in_sp, maxN, c->bf16, in0, b.out, &why))
-            if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
-        } else if (tc_prepare(L.tc, L.w, L.c0, L.c1, L.cout, L.k, L.s, L.in_sp, L.out_sp, maxN, c->bf16, in0, in1, b.raw, L.raw32, &why)) {
+      if (L.has_norm) { L.sums = c->stats_arena + off; off += (size_t)maxN * L.cout * 2; }
+      CU_TRY(cudaMalloc(&L.out, (size_t)maxN * L.cout * L.vout() * c->elt));
+      if (L.raw32) CU_TRY(cudaMalloc(&L.raw, (size_t)maxN * L.cout * L.vout() * 4)); else L.raw = L.out;
+      const bool need_s2d = L.s2d_s[0] * L.s2d_s[1] * L.s2d_s[2] > 1;
+      if (need_s2d) CU_TRY(cudaMalloc(&L.s2d, (size_t)maxN * L.cout * L.vout() * c->elt));
+    }
+    c->buffers_ready = true;
+  }
+  // ---- tcgen05 packing + tensor maps ----
+  for (int i = 0; i < nL; ++i) {
+    Layer& L = c->layers[i];
+    tc_free(L.tc);
+    std::string why;
+    if (L.kind == L_FIRST) {
+      static int allow_first = -1;
+      if (allow_first < 0) { const char* e = getenv("DWMH_TC_FIRST"); allow_first = e ? atoi(e) : 1; }
+      if (allow_first && L.k[0] == 3 && L.k[1] == 3 && L.k[2] == 3 && L.c0 == 1) {
+        std::vector<float> w27((size_t)27 * L.cout);
+        for (int co = 0; co < L.cout; ++co) for (int t = 0; t < 27; ++t) w27[(size_t)t * L.cout + co] = L.w[(size_t)co * 27 + t];
+        if (tc_prepare_first(L.tc, w27, L.cout, L.out_sp, c->bf16, L.raw, &why))
           if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
-        }
-      } else if (L.tc.enabled) {
-        if (tc_remap(L.tc, in0, in1, &why)) return fail("tcgen05 tensor maps for %s failed: %s", L.name.c_str(), why.c_str());
       }
-      b.tm0 = L.tc.tm0; b.tm1 = L.tc.tm1;
+      continue;
+    }
+    const void* in0 = c->layers[L.in0].out;
+    const void* in1 = L.in1 >= 0 ? c->layers[L.in1].out : nullptr;
+    const bool strided = L.kind == L_CONV && (L.s[0] != 1 || L.s[1] != 1 || L.s[2] != 1);
+    if (strided && c->layers[L.in0].s2d) in0 = c->layers[L.in0].s2d;
+    if (L.kind == L_TCONV) {
+      if (tc_prepare_tconv(L.tc, L.w, L.c0, L.cout, L.s, L.in_sp, maxN, c->bf16, in0, L.out, &why))
+        if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
+    } else if (tc_prepare(L.tc, L.w, L.c0, L.c1, L.cout, L.k, L.s, L.in_sp, L.out_sp, maxN, c->bf16, in0, in1, L.raw, L.raw32, &why)) {
+      if (!why.empty()) return fail("tcgen05 setup for %s failed: %s", L.name.c_str(), why.c_str());
+    }
+  }
+  // scratch for the per-CTA statistics partials of one launch (largest layer x batch size)
+  {
+    size_t need = 0;
+    for (auto& L : c->layers)
+      if (L.tc.enabled)
+        for (int nb = 1; nb <= maxN; ++nb) need = std::max(need, tc_partials_needed(L.tc.kp, nb, c->num_sms));
+    if (need > c->stat_partials_cap) {
+      free_dev(c->stat_partials); c->stat_partials = nullptr; c->stat_partials_cap = 0;
+      CU_TRY(cudaMalloc((void**)&c->stat_partials, need * sizeof(StatPartial)));
+      c->stat_partials_cap = need;
     }
   }
   // norm-on-load fusion: producer P feeds exactly one consumer, a tcgen05 layer whose shape supports the in-kernel
@@ -442,7 +424,6 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
       if (P.has_norm && !P.raw32 && uses[L.in0] == 1 && P.s2d_s[0] * P.s2d_s[1] * P.s2d_s[2] == 1 && P.cout <= 64) P.fused_norm = true;
     }
   }
-  c->active_lane = -1;
   if (!c->zs_acc) CU_TRY(cudaMalloc((void**)&c->zs_acc, 4 * sizeof(double)));
   if (!c->gauss_custom) {
     c->gauss_host.resize(c->P());
@@ -459,31 +440,13 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     CU_TRY(cudaFuncSetAttribute(tconv_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
   }
   DW_TRY(tc_init_attributes(c->bf16));
-  // The tcgen05 CTA runs with the maximum shared-memory carveout; kernels meant to run BESIDE it on the same SM
-  // (other lane, high-priority stream) must ask for the same carveout or the SM has to drain to reconfigure.
-  {
-    const int mx = cudaSharedmemCarveoutMaxShared;
-    if (c->bf16) {
-      cudaFuncSetAttribute(instnorm_lrelu_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-      cudaFuncSetAttribute(conv_first_kernel<__nv_bfloat16, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-      cudaFuncSetAttribute(conv_first_kernel<__nv_bfloat16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-      cudaFuncSetAttribute(head_softmax_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    } else {
-      cudaFuncSetAttribute(instnorm_lrelu_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-      cudaFuncSetAttribute(conv_first_kernel<__half, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-      cudaFuncSetAttribute(conv_first_kernel<__half, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-      cudaFuncSetAttribute(head_softmax_kernel<__half>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    }
-    cudaFuncSetAttribute(aggregate_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-    cudaGetLastError();
-  }
   c->committed = true;
   return 0;
 }
 
 extern "C" int dwmh_set_importance_map(dwmh_ctx* c, const float* map_host) {
   if (!c || !map_host) return fail("null argument");
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   c->gauss_host.assign(map_host, map_host + c->P());
   c->gauss_custom = true;
   if (c->gauss_dev) CU_TRY(cudaMemcpy(c->gauss_dev, c->gauss_host.data(), c->P() * sizeof(float), cudaMemcpyHostToDevice));
@@ -553,7 +516,7 @@ extern "C" int dwmh_zscore(dwmh_ctx* c, float* vol, const int8_t* seg, int64_t n
   if (mask_mode == 1 && !seg) return fail("dwmh_zscore: mask_mode 1 needs seg");
   if ((reinterpret_cast<uintptr_t>(vol) & 15) || (seg && (reinterpret_cast<uintptr_t>(seg) & 3))) return fail("dwmh_zscore: buffers must be 16-byte (vol) / 4-byte (seg) aligned");
   cudaStream_t st = (cudaStream_t)stream_;
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   if (!c->zs_acc) CU_TRY(cudaMalloc((void**)&c->zs_acc, 4 * sizeof(double)));
   CU_TRY(cudaMemsetAsync(c->zs_acc, 0, 4 * sizeof(double), st));
   const int grid = c->num_sms * 8;
@@ -575,56 +538,31 @@ extern "C" int dwmh_zscore(dwmh_ctx* c, float* vol, const int8_t* seg, int64_t n
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-// Point the layer structs at one lane's buffers / tensor maps (kernel parameters are captured by value at
-// launch, so switching views between launches on the host is safe).
-static void activate_lane(dwmh_ctx* c, int lane) {
-  if (c->active_lane == lane) return;
-  Lane& ln = c->lanes[lane];
-  for (size_t i = 0; i < c->layers.size(); ++i) {
-    Layer& L = c->layers[i];
-    const LaneLayer& b = ln.ll[i];
-    L.out = b.out; L.raw = b.raw; L.s2d = b.s2d; L.sums = b.sums;
-    if (L.tc.enabled) { L.tc.tm0 = b.tm0; L.tc.tm1 = b.tm1; L.tc.kp.out = L.kind == L_TCONV ? b.out : b.raw; }
-  }
-  c->stats_arena = ln.stats_arena; c->probs = ln.probs;
-  c->active_lane = lane;
-}
-
-// Issue-stream selection inside one forward: `tc` kernels go to st_tc, everything else to st_aux; when the
-// two differ, consecutive kernels are chained with an event (record on the previous stream, wait on the next).
-struct StreamHop {
-  cudaStream_t st_tc, st_aux, cur; Lane* ln;
-  int to(cudaStream_t want) {
-    if (want == cur) return 0;
-    cudaEvent_t e = ln->hop[ln->hop_i]; ln->hop_i = (ln->hop_i + 1) % (int)ln->hop.size();
-    if (cudaEventRecord(e, cur) != cudaSuccess || cudaStreamWaitEvent(want, e, 0) != cudaSuccess) return 1;
-    cur = want;
-    return 0;
-  }
-};
-
+// One batch of forwards on one stream.  Every conv / transposed conv is a conv3_tc_kernel launch (tcgen05) unless the layer
+// shape is unsupported or dwmh_set_force_generic is on (CUDA-core cross-check kernels).
 template <typename T>
 static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, int SY, int SZ,
-                        const SampleMeta* metas, int nb, cudaStream_t st_tc, cudaStream_t st_aux, Lane* lane, cudaStream_t* last) {
+                        const SampleMeta* metas, int nb, cudaStream_t st) {
   if (nb > c->max_batch) return fail("forward: batch %d > max_batch %d", nb, c->max_batch);
-  StreamHop hop{st_tc, st_aux, st_aux, lane};
-  cudaStream_t st = st_aux;
   CU_TRY(cudaMemsetAsync(c->stats_arena, 0, c->stats_bytes, st));
+  auto tc_timed = [&](Layer& L, auto&& launch) -> int {
+    const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
+    if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
+    DW_TRY(launch());
+    if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
+    c->launches += L.kind == L_TCONV ? 1 : 2;      // conv3_tc_kernel (+ stats_reduce_kernel)
+    return 0;
+  };
+  auto norm_of = [&](Layer& L) { return NormParams{L.sums, L.gamma_dev, L.beta_dev, L.stats_mean_var ? 0.0 : 1.0 / (double)L.vout()}; };
   for (size_t li = 0; li < c->layers.size(); ++li) {
     Layer& L = c->layers[li];
     const int taps = L.k[0] * L.k[1] * L.k[2];
-    if (L.kind == L_FIRST && L.tc.enabled && !c->force_generic) {
-      if (hop.to(st_tc)) return fail("stream hop failed");
-      st = st_tc;
+    const bool use_tc = L.tc.enabled && !c->force_generic;
+    L.stats_mean_var = use_tc && L.has_norm;
+    if (L.kind == L_FIRST && use_tc) {
       TcFirstSrc fs{src, metas, patch_mode, SY, SZ};
-      const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
-      if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
-      DW_TRY(tc_launch<T>(L.tc, nb, L.sums, c->num_sms, st, &g_err, nullptr, &fs));
-      if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
-      c->launches++;
+      DW_TRY(tc_timed(L, [&] { return tc_launch<T>(L.tc, nb, L.sums, c->stat_partials, c->num_sms, st, &g_err, nullptr, &fs); }));
     } else if (L.kind == L_FIRST) {
-      if (hop.to(st_aux)) return fail("stream hop failed");
-      st = st_aux;
       FirstConvParams p;
       p.src = src; p.metas = metas; p.w = L.w_dev; p.out = L.raw; p.sums = L.sums; p.patch_mode = patch_mode;
       p.SX = SX; p.SY = SY; p.SZ = SZ; p.px = L.out_sp[0]; p.py = L.out_sp[1]; p.pz = L.out_sp[2];
@@ -637,48 +575,27 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
       } else if (taps == 27) conv_first_kernel<T, true><<<grid, 256, smem, st>>>(p);
       else conv_first_kernel<T, false><<<grid, 256, smem, st>>>(p);
       c->launches++;
+    } else if (L.kind == L_CONV && use_tc) {
+      Layer& P = c->layers[L.in0];
+      NormParams pn = norm_of(P);
+      TcXform xf{pn.sums, pn.gamma, pn.beta, pn.inv_count, P.out};
+      DW_TRY(tc_timed(L, [&] { return tc_launch<T>(L.tc, nb, L.sums, c->stat_partials, c->num_sms, st, &g_err, P.fused_norm ? &xf : nullptr); }));
     } else if (L.kind == L_CONV) {
-      bool done = false;
-      if (L.tc.enabled && !c->force_generic) {
-        if (hop.to(st_tc)) return fail("stream hop failed");
-        st = st_tc;
-        const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
-        if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
-        {
-          Layer& P = c->layers[L.in0];
-          TcXform xf{P.sums, P.gamma_dev, P.beta_dev, 1.0f / (float)P.vout(), P.out};
-          DW_TRY(tc_launch<T>(L.tc, nb, L.sums, c->num_sms, st, &g_err, P.fused_norm ? &xf : nullptr));
-        }
-        if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
-        done = true; c->launches++;
-      }
-      if (!done) {
-        if (hop.to(st_aux)) return fail("stream hop failed");
-        st = st_aux;
-        ConvParams p;
-        p.in0 = c->layers[L.in0].out; p.C0 = L.c0;
-        p.in1 = L.in1 >= 0 ? c->layers[L.in1].out : nullptr; p.C1 = L.c1;
-        p.w = L.w_dev; p.out = L.raw; p.out32 = L.raw32 ? 1 : 0; p.sums = L.sums; p.N = nb;
-        p.Di = L.in_sp[0]; p.Hi = L.in_sp[1]; p.Wi = L.in_sp[2]; p.Do = L.out_sp[0]; p.Ho = L.out_sp[1]; p.Wo = L.out_sp[2];
-        p.Cout = L.cout; p.kd = L.k[0]; p.kh = L.k[1]; p.kw = L.k[2]; p.sd = L.s[0]; p.sh = L.s[1]; p.sw = L.s[2];
-        const int tiles = ((p.Do + GC_TD - 1) / GC_TD) * ((p.Ho + GC_TH - 1) / GC_TH) * ((p.Wo + GC_TW - 1) / GC_TW);
-        const int ed = (GC_TD - 1) * p.sd + p.kd, eh = (GC_TH - 1) * p.sh + p.kh, ew = (GC_TW - 1) * p.sw + p.kw;
-        const size_t smem = (size_t)ed * eh * ew * 16 + (size_t)taps * 8 * GC_COB * sizeof(float);
-        dim3 grid(tiles, L.cout / GC_COB, nb);
-        conv_generic_kernel<T><<<grid, 128, smem, st>>>(p);
-        c->launches++;
-      }
-    } else if (L.tc.enabled && !c->force_generic) {
-      if (hop.to(st_tc)) return fail("stream hop failed");
-      st = st_tc;
-      const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
-      if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
-      DW_TRY(tc_launch<T>(L.tc, nb, nullptr, c->num_sms, st, &g_err));
-      if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
+      ConvParams p;
+      p.in0 = c->layers[L.in0].out; p.C0 = L.c0;
+      p.in1 = L.in1 >= 0 ? c->layers[L.in1].out : nullptr; p.C1 = L.c1;
+      p.w = L.w_dev; p.out = L.raw; p.out32 = L.raw32 ? 1 : 0; p.sums = L.sums; p.N = nb;
+      p.Di = L.in_sp[0]; p.Hi = L.in_sp[1]; p.Wi = L.in_sp[2]; p.Do = L.out_sp[0]; p.Ho = L.out_sp[1]; p.Wo = L.out_sp[2];
+      p.Cout = L.cout; p.kd = L.k[0]; p.kh = L.k[1]; p.kw = L.k[2]; p.sd = L.s[0]; p.sh = L.s[1]; p.sw = L.s[2];
+      const int tiles = ((p.Do + GC_TD - 1) / GC_TD) * ((p.Ho + GC_TH - 1) / GC_TH) * ((p.Wo + GC_TW - 1) / GC_TW);
+      const int ed = (GC_TD - 1) * p.sd + p.kd, eh = (GC_TH - 1) * p.sh + p.kh, ew = (GC_TW - 1) * p.sw + p.kw;
+      const size_t smem = (size_t)ed * eh * ew * 16 + (size_t)taps * 8 * GC_COB * sizeof(float);
+      dim3 grid(tiles, L.cout / GC_COB, nb);
+      conv_generic_kernel<T><<<grid, 128, smem, st>>>(p);
       c->launches++;
+    } else if (use_tc) {
+      DW_TRY(tc_timed(L, [&] { return tc_launch<T>(L.tc, nb, nullptr, nullptr, c->num_sms, st, &g_err); }));
     } else {
-      if (hop.to(st_aux)) return fail("stream hop failed");
-      st = st_aux;
       TConvParams p;
       p.in = c->layers[L.in0].out; p.out = L.out; p.w = L.w_dev; p.N = nb; p.Cin = L.c0; p.Cout = L.cout;
       p.Di = L.in_sp[0]; p.Hi = L.in_sp[1]; p.Wi = L.in_sp[2]; p.sd = L.s[0]; p.sh = L.s[1]; p.sw = L.s[2];
@@ -688,46 +605,35 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
     }
     c->conv_flops += L.flops_per_sample() * nb;
     if (L.has_norm && (int)li != c->last_conv && !(L.fused_norm && !c->force_generic)) {
-      if (hop.to(st_aux)) return fail("stream hop failed");
-      st = st_aux;
-      NormParams np{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
       const int64_t V = L.vout();
       const int gx = (int)std::min<int64_t>((V / 2 + 255) / 256, 1024);      // a thread handles voxel pairs (256-bit accesses)
       dim3 grid(std::max(gx, 1), nb * (L.cout >> 3));
       S2dParams sp{L.s2d, L.out_sp[0], L.out_sp[1], L.out_sp[2], L.s2d_s[0], L.s2d_s[1], L.s2d_s[2]};
-      instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, np, L.cout, V, sp);
+      instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, norm_of(L), L.cout, V, sp);
       c->launches++;
     }
   }
   // head: norm-on-load + 1x1x1 + softmax
-  if (hop.to(st_aux)) return fail("stream hop failed");
-  st = st_aux;
   Layer& L = c->layers[c->last_conv];
-  NormParams np{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
   dim3 grid((unsigned)((L.vout() + 255) / 256), nb);
-  head_softmax_kernel<T><<<grid, 256, 4 * L.cout * sizeof(float), st>>>((const T*)L.out, np, c->w_head_dev, c->probs, L.cout, L.vout());
+  head_softmax_kernel<T><<<grid, 256, 4 * L.cout * sizeof(float), st>>>((const T*)L.out, norm_of(L), c->w_head_dev, c->probs, L.cout, L.vout());
   c->launches++;
   c->conv_flops += 2.0 * L.vout() * L.cout * c->d.num_classes * nb;
   CU_TRY(cudaGetLastError());
-  if (last) *last = hop.cur;
   return 0;
 }
 
-// single-stream form (hooks) and two-stream form (lanes)
-static int forward(dwmh_ctx* c, const float* src, int patch_mode, int SX, int SY, int SZ, const SampleMeta* metas, int nb,
-                   cudaStream_t st_tc, cudaStream_t st_aux = nullptr, Lane* lane = nullptr, cudaStream_t* last = nullptr) {
-  if (!lane) st_aux = st_tc;
-  return c->bf16 ? forward_impl<__nv_bfloat16>(c, src, patch_mode, SX, SY, SZ, metas, nb, st_tc, st_aux, lane, last)
-                 : forward_impl<__half>(c, src, patch_mode, SX, SY, SZ, metas, nb, st_tc, st_aux, lane, last);
+static int forward(dwmh_ctx* c, const float* src, int patch_mode, int SX, int SY, int SZ, const SampleMeta* metas, int nb, cudaStream_t st) {
+  return c->bf16 ? forward_impl<__nv_bfloat16>(c, src, patch_mode, SX, SY, SZ, metas, nb, st)
+                 : forward_impl<__half>(c, src, patch_mode, SX, SY, SZ, metas, nb, st);
 }
 
 extern "C" int dwmh_forward_patches(dwmh_ctx* c, const float* patches, int32_t n, float* probs_out, void* stream_) {
   if (!c || !patches || !probs_out) return fail("dwmh_forward_patches: null argument");
   if (!c->committed) return fail("dwmh_forward_patches: weights not committed");
   cudaStream_t st = (cudaStream_t)stream_;
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   const int64_t P = c->P();
-  activate_lane(c, 0);
   for (int b = 0; b < n; b += c->max_batch) {
     const int nb = std::min(c->max_batch, n - b);
     DW_TRY(forward(c, patches + (size_t)b * P, 1, 0, 0, 0, nullptr, nb, st));
@@ -738,7 +644,6 @@ extern "C" int dwmh_forward_patches(dwmh_ctx* c, const float* patches, int32_t n
 
 extern "C" int dwmh_debug_layer_output(dwmh_ctx* c, int32_t li, float* out, int64_t capacity, int32_t dims[5], void* stream_) {
   if (!c || li < 0 || li >= (int)c->layers.size()) return fail("dwmh_debug_layer_output: bad layer index");
-  activate_lane(c, 0);
   Layer& L = c->layers[li];
   const int n = c->max_batch;
   dims[0] = n; dims[1] = L.cout; dims[2] = L.out_sp[0]; dims[3] = L.out_sp[1]; dims[4] = L.out_sp[2];
@@ -747,10 +652,10 @@ extern "C" int dwmh_debug_layer_output(dwmh_ctx* c, int32_t li, float* out, int6
   int nn = n;
   if (capacity < need) { nn = (int)(capacity / ((int64_t)L.cout * L.vout())); dims[0] = nn; if (nn <= 0) return fail("capacity too small"); }
   cudaStream_t st = (cudaStream_t)stream_;
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   // the last conv is kept raw (the head normalises on load): normalise here for a uniform view
-  NormParams np{nullptr, nullptr, nullptr, 0.f};
-  if ((int)li == c->last_conv || (L.fused_norm && !c->force_generic)) np = NormParams{L.sums, L.gamma_dev, L.beta_dev, 1.0f / (float)L.vout()};
+  NormParams np{nullptr, nullptr, nullptr, 0.0};
+  if ((int)li == c->last_conv || (L.fused_norm && !c->force_generic)) np = NormParams{L.sums, L.gamma_dev, L.beta_dev, L.stats_mean_var ? 0.0 : 1.0 / (double)L.vout()};
   if (c->bf16) unpack_layer_kernel<__nv_bfloat16><<<c->num_sms * 4, 256, 0, st>>>((const __nv_bfloat16*)L.out, np, out, nn, L.cout, L.vout());
   else unpack_layer_kernel<__half><<<c->num_sms * 4, 256, 0, st>>>((const __half*)L.out, np, out, nn, L.cout, L.vout());
   CU_TRY(cudaGetLastError());
@@ -767,7 +672,7 @@ extern "C" int dwmh_predict_3d(dwmh_ctx* c, const float* vol, int32_t X, int32_t
   if (!c->committed) return fail("dwmh_predict_3d: weights not committed");
   if (step_size > 1.0) return fail("step_size must be smaller than 1");
   cudaStream_t st = (cudaStream_t)stream_;
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   const int32_t* ps = c->d.patch_size;
   std::vector<int> steps[3];
   const int img[3] = {X, Y, Z};
@@ -813,43 +718,23 @@ extern "C" int dwmh_predict_3d(dwmh_ctx* c, const float* vol, int32_t X, int32_t
     while (c->tcev.size() < 128) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); c->tcev.push_back(e); }
     c->tcev_used = 0; c->tc_ms = 0; c->tc_flops = 0; c->tc_launches = 0;
   }
-  // Lanes: batch b runs its forwards on lane (b % nlanes)'s stream; the overlap-add of every tile is issued on
-  // the caller's stream in tile order (deterministic).  Profiling mode serialises everything on one lane.
-  const int nl = c->stage_timing ? 1 : (int)c->lanes.size();
-  CU_TRY(cudaEventRecord(c->ev_start, st));
-  for (int l = 0; l < nl; ++l) {
-    CU_TRY(cudaStreamWaitEvent(c->lanes[l].stream, c->ev_start, 0));
-    CU_TRY(cudaStreamWaitEvent(c->lanes[l].stream_aux, c->ev_start, 0));
-    c->lanes[l].agg_pending = false;
-  }
-  int bi = 0;
-  for (int t0 = 0; t0 < nt; t0 += tiles_per_batch, ++bi) {
+  // Batches of forwards and the overlap-add of their tiles alternate on the caller's stream, tiles in order (deterministic).
+  for (int t0 = 0; t0 < nt; t0 += tiles_per_batch) {
     const int tb = std::min(tiles_per_batch, nt - t0);
-    const int l = bi % nl;
-    Lane& ln = c->lanes[l];
-    if (ln.agg_pending) CU_TRY(cudaStreamWaitEvent(ln.stream_aux, ln.agg_done, 0));     // previous probs of this lane consumed
-    activate_lane(c, l);
-    const bool split = !c->stage_timing && c->split_streams;
-    cudaStream_t s_tc = split ? ln.stream : ln.stream_aux, s_last = ln.stream_aux;
-    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[0], ln.stream_aux));
-    DW_TRY(forward(c, vol, 0, X, Y, Z, c->metas_dev + (size_t)t0 * M, tb * M, s_tc, ln.stream_aux, &ln, &s_last));
-    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[1], s_last));
-    CU_TRY(cudaEventRecord(ln.fwd_done, s_last));
-    CU_TRY(cudaStreamWaitEvent(st, ln.fwd_done, 0));
-    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[3], st));
+    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[0], st));
+    DW_TRY(forward(c, vol, 0, X, Y, Z, c->metas_dev + (size_t)t0 * M, tb * M, st));
+    if (c->stage_timing) CU_TRY(cudaEventRecord(c->ev[1], st));
     for (int t = 0; t < tb; ++t) {
       aggregate_tile_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(
-          ln.probs + (size_t)t * M * 2 * P, c->metas_dev + (size_t)(t0 + t) * M, M, gauss ? c->gauss_dev : nullptr,
+          c->probs + (size_t)t * M * 2 * P, c->metas_dev + (size_t)(t0 + t) * M, M, gauss ? c->gauss_dev : nullptr,
           agg, wgt, ps[0], ps[1], ps[2], X, Y, Z);
       c->launches++;
     }
-    CU_TRY(cudaEventRecord(ln.agg_done, st));
-    ln.agg_pending = true;
     if (c->stage_timing) {
       CU_TRY(cudaEventRecord(c->ev[2], st));
       CU_TRY(cudaEventSynchronize(c->ev[2]));
       float a = 0, b = 0;
-      cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); cudaEventElapsedTime(&b, c->ev[3], c->ev[2]);
+      cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
       conv_ms += a; agg_ms += b;
       for (int i = 0; i + 1 < c->tcev_used; i += 2) { float t = 0; cudaEventElapsedTime(&t, c->tcev[i], c->tcev[i + 1]); c->tc_ms += t; }
       c->tcev_used = 0;
@@ -864,7 +749,7 @@ extern "C" int dwmh_finalize(dwmh_ctx* c, const float* agg, const float* wgt, fl
                              int32_t X, int32_t Y, int32_t Z, void* stream_) {
   if (!c || !agg || !wgt) return fail("dwmh_finalize: null argument");
   cudaStream_t st = (cudaStream_t)stream_;
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   const int64_t V = (int64_t)X * Y * Z;
   finalize_kernel<<<c->num_sms * 8, 256, 0, st>>>(agg, wgt, softmax, seg, V);
   c->launches++;
@@ -874,7 +759,7 @@ extern "C" int dwmh_finalize(dwmh_ctx* c, const float* agg, const float* wgt, fl
 
 extern "C" int dwmh_axpy(dwmh_ctx* c, float* acc, const float* x, float alpha, int64_t n, void* stream_) {
   if (!c || !acc || !x) return fail("dwmh_axpy: null argument");
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   axpy_kernel<<<c->num_sms * 8, 256, 0, (cudaStream_t)stream_>>>(acc, x, alpha, n);
   c->launches++;
   CU_TRY(cudaGetLastError());
@@ -883,7 +768,7 @@ extern "C" int dwmh_axpy(dwmh_ctx* c, float* acc, const float* x, float alpha, i
 
 extern "C" int dwmh_argmax2(dwmh_ctx* c, const float* p, uint8_t* seg, int64_t V, void* stream_) {
   if (!c || !p || !seg) return fail("dwmh_argmax2: null argument");
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   argmax2_kernel<<<c->num_sms * 8, 256, 0, (cudaStream_t)stream_>>>(p, seg, V);
   c->launches++;
   CU_TRY(cudaGetLastError());
@@ -906,7 +791,7 @@ static int grow(V** p, size_t* cap, size_t need) {
 // checkpoint ensemble of masked background probabilities (DCNN_multistage.py:102-125)
 extern "C" int dwmh_ensemble_masked_add(dwmh_ctx* c, float* acc, const float* bg_softmax, const float* valid_mask, int64_t n, void* stream_) {
   if (!c || !acc || !bg_softmax) return fail("dwmh_ensemble_masked_add: null argument");
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   ensemble_masked_add_kernel<<<c->num_sms * 8, 256, 0, (cudaStream_t)stream_>>>(acc, bg_softmax, valid_mask, n);
   c->launches++;
   CU_TRY(cudaGetLastError());
@@ -915,7 +800,7 @@ extern "C" int dwmh_ensemble_masked_add(dwmh_ctx* c, float* acc, const float* bg
 extern "C" int dwmh_ensemble_refine(dwmh_ctx* c, float* acc, int32_t k, uint8_t* label, int64_t n, void* stream_) {
   if (!c || !acc) return fail("dwmh_ensemble_refine: null argument");
   if (k <= 0) return fail("dwmh_ensemble_refine: k must be positive");
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   ensemble_refine_kernel<<<c->num_sms * 8, 256, 0, (cudaStream_t)stream_>>>(acc, (float)k, label, n);
   c->launches++;
   CU_TRY(cudaGetLastError());
@@ -929,7 +814,7 @@ extern "C" int dwmh_remove_sparks(dwmh_ctx* c, const uint8_t* seg, int32_t X, in
   if (X <= 0 || Y <= 0 || Z <= 0) return fail("dwmh_remove_sparks: empty volume");
   const int64_t V = (int64_t)X * Y * Z;
   if (V >= (int64_t)1 << 31) return fail("dwmh_remove_sparks: volume of %lld voxels exceeds the 32-bit label range", (long long)V);
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   DW_TRY(grow(&c->ccl_labels, &c->ccl_cap_l, (size_t)V));
   DW_TRY(grow(&c->ccl_sizes, &c->ccl_cap_s, (size_t)V));
   cudaStream_t st = (cudaStream_t)stream_;
@@ -950,7 +835,7 @@ extern "C" int dwmh_predict_volume_host(dwmh_ctx* c, const float* vol_host, int3
   if (!c || !vol_host) return fail("dwmh_predict_volume_host: null argument");
   if (zscore_mask_mode == 1) return fail("dwmh_predict_volume_host: mask_mode 1 needs a device seg; use dwmh_zscore");
   cudaStream_t st = (cudaStream_t)stream_;
-  CU_TRY(cudaSetDevice(c->device));
+  DEV_GUARD(c->device);
   const int64_t V = (int64_t)X * Y * Z;
   const int32_t* ps = c->d.patch_size;
   // a10 pad_nd_image: below = diff/2, above = diff/2 + diff%2

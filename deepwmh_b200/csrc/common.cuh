@@ -87,24 +87,44 @@ struct SampleMeta {
   int32_t flip;           // bit0: flip axis 2 (z), bit1: axis 1 (y), bit2: axis 0 (x)   == mirror index m
 };
 
-// InstanceNorm statistics of one layer: sums[(n*C + c)*2 + {0,1}] = {sum y, sum y^2} in fp64.
+// InstanceNorm statistics of one layer, fp64, two formats:
+//   inv_count  > 0: sums[(n*C + c)*2 + {0,1}] = {sum y, sum y^2}          (CUDA-core cross-check kernels: fp64 atomics)
+//   inv_count == 0: sums[(n*C + c)*2 + {0,1}] = {mean, biased variance}    (tcgen05 path: written by stats_reduce_kernel from
+//                   the per-CTA Welford partials in a fixed order -- deterministic and free of E[x^2] - E[x]^2 cancellation)
 struct NormParams {
   const double* sums;     // nullptr => identity (no norm / activation)
   const float* gamma;
   const float* beta;
-  float inv_count;        // 1 / (D*H*W)
+  double inv_count;       // 1 / (D*H*W), or 0 (see above)
 };
 
 // a = gamma / sqrt(var + eps), b = beta - mean * a   (InstanceNorm3d eps 1e-5, biased variance)
 __device__ __forceinline__ void norm_coeffs(const NormParams& np, int n, int C, int c, float& a, float& b) {
   const double s1 = np.sums[((size_t)n * C + c) * 2 + 0];
   const double s2 = np.sums[((size_t)n * C + c) * 2 + 1];
-  const double mean = s1 * (double)np.inv_count;
-  double var = s2 * (double)np.inv_count - mean * mean;
+  double mean = s1, var = s2;
+  if (np.inv_count != 0.0) {
+    mean = s1 * np.inv_count;
+    var = s2 * np.inv_count - mean * mean;
+  }
   var = var > 0.0 ? var : 0.0;
   const double inv = rsqrt(var + 1e-5);
   a = (float)((double)np.gamma[c] * inv);
   b = (float)((double)np.beta[c] - mean * (double)np.gamma[c] * inv);
+}
+
+// One (count, mean, M2 = sum (x - mean)^2) partial of the tcgen05 conv epilogue: one per (work item, epilogue warp, channel).
+struct StatPartial { float n, mean, m2, pad; };
+
+// Chan's pairwise update of (n, mean, M2) with a second partial; exact in real arithmetic, well conditioned in floating point.
+template <typename F>
+__device__ __forceinline__ void stat_merge(F& n, F& mean, F& m2, F nb, F meanb, F m2b) {
+  const F nt = n + nb;
+  const F w = nt > (F)0 ? nb / nt : (F)0;
+  const F d = meanb - mean;
+  mean = mean + d * w;
+  m2 = m2 + m2b + d * d * n * w;
+  n = nt;
 }
 
 }  // namespace dwmh

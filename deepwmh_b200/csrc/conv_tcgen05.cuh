@@ -54,20 +54,18 @@ constexpr int TC_FIRST_STAGE_BYTES = 8 * 128 * 16;     // im2col operand of one 
 struct TcClassDesc { int tapmask, jlo, jcnt, tile0; };
 
 struct TcKParams {
-  const void* wpack; void* out; double* sums;
+  const void* wpack; void* out; StatPartial* partials;   // partials: [item][4 epilogue warps][CB] (count, mean, M2)
   int C0, C1, Cout, CB, KC, nkc, nkc0;
   int nclass, Jlo, Jhi, jmax, tiles_per_kc, Din;
   int out32;                                 // raw output stored as fp32 instead of T
   int s222;                                  // stride (2,2,2): the standard 8 parity classes (straight-line issue path)
-  int mcast;                                 // debug: 0 = cluster launch but every CTA loads its own weight tiles
-  int cluster;                               // 2: CTA pairs (thread-block cluster) share every streamed weight tile by TMA multicast
   int tconv, CBt, osd, osh, osw, Cout_t;   // transposed-conv mode: CB = osd*osh*osw * CBt, scatter epilogue
   TcClassDesc cls[8];
   int D, H, W, tilesH, tilesW, ZB, nzb, ncb;
   int SA, NB, resident, R, fmt;
   // norm-on-load (XFORM kernels): the input tensor is the producer's RAW fp16 output; InstanceNorm + LeakyReLU of the
   // producer are applied to each landed plane in shared memory by the two producer warps before the MMA reads it
-  const double* xf_sums; const float* xf_gamma; const float* xf_beta; float xf_inv_count; int xform; const void* xf_src;
+  const double* xf_sums; const float* xf_gamma; const float* xf_beta; double xf_inv_count; int xform; const void* xf_src;
   // FIRST kernels (Cin = 1 first conv): loader warps build an im2col operand from the fp32 volume / patches
   const float* fc_src; const SampleMeta* fc_metas; int fc_patch_mode, fc_SY, fc_SZ, first;
   int G;              // work-item pipelines ("groups") per CTA: 2 = two tiles share the resident weights, each with 256 TMEM columns
@@ -76,6 +74,30 @@ struct TcKParams {
   int dbg;            // profiling knobs (env DWMH_TC_DEBUG): 1 = no activation TMA, 2 = no MMA, 4 = no epilogue stores
   uint32_t a_stage_bytes, b_tile_bytes, off_b, off_bar;
 };
+
+// Ordered second stage: every (sample, channel) combines the partials of its work items in index order, in fp64.
+// partials: [item][4 warps][CB]; the items of (n, cb) are the contiguous range [(n*ncb + cb) * ipb, +ipb).
+// grid = nb * ncb blocks of CB * jn threads (c fastest -> coalesced 16-byte reads); out = {mean, biased variance}.
+__global__ void __launch_bounds__(256) stats_reduce_kernel(const StatPartial* __restrict__ partials, double* __restrict__ out,
+                                                           int ncb, int CB, int Cout, int ipb, int jn) {
+  __shared__ double sh[3][256];
+  const int n = blockIdx.x / ncb, cb = blockIdx.x % ncb;
+  const int c = threadIdx.x % CB, j = threadIdx.x / CB;
+  const StatPartial* base = partials + (size_t)blockIdx.x * ipb * 4 * CB + c;
+  double cn = 0.0, cm = 0.0, cq = 0.0;
+  for (int p = j; p < ipb * 4; p += jn) {
+    const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * CB);
+    stat_merge<double>(cn, cm, cq, (double)v.x, (double)v.y, (double)v.z);
+  }
+  sh[0][threadIdx.x] = cn; sh[1][threadIdx.x] = cm; sh[2][threadIdx.x] = cq;
+  __syncthreads();
+  if (j == 0) {
+    for (int jj = 1; jj < jn; ++jj) stat_merge<double>(cn, cm, cq, sh[0][jj * CB + c], sh[1][jj * CB + c], sh[2][jj * CB + c]);
+    double* o = out + ((size_t)n * Cout + (size_t)cb * CB + c) * 2;
+    o[0] = cm;
+    o[1] = cn > 0.0 ? cq / cn : 0.0;
+  }
+}
 
 // Ring-buffer cursor without div/mod.
 struct RingPos {
@@ -133,12 +155,10 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const uint32_t a_ready = acc_empty + 8u * R;          // XFORM: plane transformed, ready for the MMA
   const uint32_t a_mma = (XFORM || FIRST) ? a_ready : a_full;      // what the MMA issuer waits on
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * nbar * p.G);
-  float* s_stat = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)g * 2 * CB;   // [2][CB] per group
   float* s_coef = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)g * 2 * 64;   // XFORM: a[64], b[64]
   float* s_slice = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)p.G * 2 * 64 + (size_t)g * 4 * TC_FIRST_SLICE;   // FIRST: 4-slot ring of haloed input slices
   const uint32_t smem_a = smem_base + (uint32_t)g * SA * p.a_stage_bytes;          // this group's activation ring
-  // UMMA shared-memory descriptors hold a 14-bit (address >> 4): CTA-relative.  In a cluster launch the shared::cta window of
-  // rank > 0 sits above 256 KB in the 32-bit shared address space, so descriptor arithmetic uses the masked offsets.
+  // UMMA shared-memory descriptors hold a 14-bit (address >> 4): descriptor arithmetic uses the masked offsets
   const uint32_t smem_a_d = smem_a & 0x3FFFFu, smem_b_d = (smem_base + p.off_b) & 0x3FFFFu;
   const uint32_t s_full = smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + (uint32_t)g * 64u, s_empty = s_full + 32u;   // FIRST: slice ring barriers
 
@@ -159,14 +179,11 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tc::mbar_init(smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + gg * 64 + 8 * s_, 1);
           tc::mbar_init(smem_base + p.off_bar + TC_SMEM_RESERVED_FIRST - 128 + gg * 64 + 32 + 8 * s_, 2);
         }
-    if (p.cluster > 1)
-      for (uint32_t s_ = 0; s_ < NB; ++s_) tc::mbar_init(smem_base + p.off_bar + TC_SMEM_RESERVED - 512 + 8 * s_, p.cluster - 1);
     const uint32_t nactive = (uint32_t)min(p.G, p.total_items - (int)blockIdx.x * p.G);      // groups of this CTA that have a tile
     for (uint32_t s_ = 0; s_ < NB; ++s_) { tc::mbar_init(b_full + 8 * s_, 1); tc::mbar_init(b_empty + 8 * s_, nactive); }
     tc::fence_barrier_init();
   }
   if (warp_abs == 1) tc::tmem_alloc(tc::smem_u32(tmem_ptr_smem), 512);
-  if constexpr (!TCONV) for (int i = threadIdx.x; i < 2 * (int)CB * p.G; i += blockDim.x) (s_stat - (size_t)g * 2 * CB)[i] = 0.f;
   if constexpr (XFORM) {
     const int tl = threadIdx.x - g * TPG;          // each group: coefficients of ITS sample
     if (tl < p.C0 && !idle) {
@@ -179,7 +196,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  if (p.cluster > 1) tc::cluster_sync();          // the peer's barriers exist before anyone arrives on them remotely
   const uint32_t tmem = *tmem_ptr_smem + (uint32_t)g * 256u;       // group 1 owns TMEM columns 256..511
   const bool prof_on = (p.dbg & 8) != 0;
   long long w0_ = 0, w1_ = 0, w2_ = 0, w3_ = 0;      // profiling (dbg & 8): barrier waits, issue bursts, general-path time
@@ -409,7 +425,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
         }
     } else if (g == 0) {     // streamed weight tiles are shared by the groups of the CTA (same cout block, same plane range)
-      const uint32_t crank = p.cluster > 1 ? tc::cluster_ctarank() : 0;
       RingPos b;
       for (int t = z_lo - p.Jhi; t <= z_end - 1 - p.Jlo; ++t) {
         if (t < 0 || t >= p.Din) continue;
@@ -420,18 +435,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             for (int ti = 0; ti < ntaps; ++ti) {
               const int tile = kc * p.tiles_per_kc + p.cls[c].tile0 + ti;
               DWMH_TIMED_WAIT(w0_, tc::mbar_wait(b_empty + 8 * b.idx, b.phase ^ 1, 2));
-              if (p.cluster > 1 && p.mcast) {
-                // CTA pair: every CTA arms its own b_full, rank 1 then tells rank 0 that its slot is free, rank 0 issues ONE
-                // multicast copy that lands in both CTAs (half the L2 weight traffic of the streamed layers)
-                const uint32_t peer_empty = smem_base + p.off_bar + TC_SMEM_RESERVED - 512 + 8 * b.idx;
-                if (leader) tc::mbar_arrive_expect_tx(b_full + 8 * b.idx, p.b_tile_bytes);
-                __syncwarp();
-                if (crank != 0) { if (leader) tc::mbar_arrive_remote(peer_empty, 0); }
-                else {
-                  DWMH_TIMED_WAIT(w0_, tc::mbar_wait_cluster(peer_empty, b.phase, 12));
-                  if (leader) tc::bulk_load_multicast(smem_base + p.off_b + b.idx * p.b_tile_bytes, wsrc + (size_t)tile * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * b.idx, (uint16_t)((1u << p.cluster) - 1));
-                }
-              } else if (leader) {
+              if (leader) {
                 tc::mbar_arrive_expect_tx(b_full + 8 * b.idx, p.b_tile_bytes);
                 tc::bulk_load(smem_base + p.off_b + b.idx * p.b_tile_bytes, wsrc + (size_t)tile * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * b.idx);
               }
@@ -863,10 +867,18 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         if (++slot == R) { slot = 0; phase ^= 1; }
       }
     } else {
+    // InstanceNorm statistics (deterministic, no E[x^2] - E[x]^2 cancellation).  Every epilogue warp leaves one
+    // (count, mean, M2) partial per channel in p.partials; stats_reduce_kernel combines them in a fixed order in fp64.
+    //   SMALL_CB (CB <= 32): per-thread Welford recurrences for the thread's row over the planes (rs = mean, rq = M2), one
+    //     transposing Chan reduction over the 32 rows at the end of the CTA;
+    //   else: per plane a transposing shuffle reduction of (x - pivot), (x - pivot)^2 over the warp's 32 rows, the pivot
+    //     being the running mean of the column (broadcast from its owner lane), merged into the lane's running (mean, M2).
     constexpr int NACC = SMALL_CB ? 32 : 8;
-    float rs[NACC], rq[NACC];      // SMALL_CB: per-thread per-channel running sums; else per-lane column totals
+    float rs[NACC], rq[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+    float cnt = 0.f;                                                          // SMALL_CB: planes of this row; else: values per column so far
+    const float nvw = (float)__popc(__ballot_sync(0xffffffffu, valid));       // valid rows of this warp
     const size_t V = (size_t)p.D * p.H * p.W;
     uint4* out_base = reinterpret_cast<uint4*>(p.out) + ((size_t)n * (p.Cout >> 3) + (size_t)cb * (CB >> 3)) * V;
     uint32_t slot = 0, phase = 0;
@@ -874,6 +886,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       DWMH_TIMED_WAIT(w0_, tc::mbar_wait(acc_full + 8 * slot, phase, 7));
       tc::tc_fence_after();
       uint4* outp = out_base + ((size_t)zo * p.H + h) * p.W + w;
+      float wgt_new, cnt_prev = cnt;
+      if constexpr (SMALL_CB) { cnt += 1.f; wgt_new = __frcp_rn(cnt); }
+      else { cnt += nvw; wgt_new = nvw > 0.f ? __fdividef(nvw, cnt) : 0.f; }
 #pragma unroll
       for (int ch = 0; ch < (SMALL_CB ? 2 : 8); ++ch) {
         if (ch < nch) {
@@ -898,12 +913,20 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if constexpr (SMALL_CB) {
             if (valid) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) { rs[ch * 16 + i] += a[i]; rq[ch * 16 + i] = fmaf(a[i], a[i], rq[ch * 16 + i]); }
+              for (int i = 0; i < 16; ++i) {
+                const float d = a[i] - rs[ch * 16 + i];
+                rs[ch * 16 + i] = fmaf(d, wgt_new, rs[ch * 16 + i]);
+                rq[ch * 16 + i] = fmaf(d, a[i] - rs[ch * 16 + i], rq[ch * 16 + i]);
+              }
             }
           } else {
             float b[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { a[i] = valid ? a[i] : 0.f; b[i] = a[i] * a[i]; }
+            for (int i = 0; i < 16; ++i) {
+              const float piv = __shfl_sync(0xffffffffu, rs[ch], i);          // running mean of column i lives in lanes i, i + 16
+              a[i] = valid ? a[i] - piv : 0.f;
+              b[i] = a[i] * a[i];
+            }
             // transposing butterfly: afterwards lane l holds the 32-row total of column (l & 15)
 #pragma unroll
             for (int k = 8; k >= 1; k >>= 1) {
@@ -916,8 +939,13 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 b[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, k);
               }
             }
-            rs[ch] += a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16);
-            rq[ch] += b[0] + __shfl_xor_sync(0xffffffffu, b[0], 16);
+            const float S = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16), Q = b[0] + __shfl_xor_sync(0xffffffffu, b[0], 16);
+            if (nvw > 0.f) {
+              // this plane's block: nvw values, mean = pivot + S / nvw, M2 = Q - S^2 / nvw; the pivot IS the running mean
+              const float dm = S / nvw;
+              rq[ch] += fmaf(-S, dm, Q) + dm * dm * cnt_prev * wgt_new;
+              rs[ch] = fmaf(dm, wgt_new, rs[ch]);
+            }
           }
         }
       }
@@ -926,33 +954,44 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       if (lane == 0) tc::mbar_arrive(acc_empty + 8 * slot);
       if (++slot == R) { slot = 0; phase ^= 1; }
     }
+    StatPartial* pout = p.partials + ((size_t)(blockIdx.x * p.G + g) * 4 + q) * CB;
     if constexpr (SMALL_CB) {
-      // one transposing reduction for the whole CTA lifetime
+      // one transposing reduction for the whole CTA lifetime: Chan's merge of the rows' (count, mean, M2)
+      const float n_row = valid ? cnt : 0.f;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         if (ch < nch) {
           float a[16], b[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { a[i] = rs[ch * 16 + i]; b[i] = rq[ch * 16 + i]; }
+          float nn = n_row;
 #pragma unroll
           for (int k = 8; k >= 1; k >>= 1) {
             const bool up = (lane & k) != 0;
+            const float np_ = __shfl_xor_sync(0xffffffffu, nn, k);
+            const float nt = nn + np_, wp = nt > 0.f ? np_ / nt : 0.f;
 #pragma unroll
             for (int i = 0; i < k; ++i) {
               const float sa_ = up ? a[i] : a[i + k], ka_ = up ? a[i + k] : a[i];
               const float sb_ = up ? b[i] : b[i + k], kb_ = up ? b[i + k] : b[i];
-              a[i] = ka_ + __shfl_xor_sync(0xffffffffu, sa_, k);
-              b[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, k);
+              const float pm = __shfl_xor_sync(0xffffffffu, sa_, k), pq = __shfl_xor_sync(0xffffffffu, sb_, k);
+              const float d = pm - ka_;
+              a[i] = fmaf(d, wp, ka_);
+              b[i] = kb_ + pq + d * d * nn * wp;
             }
+            nn = nt;
           }
-          const float ts = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16), tq = b[0] + __shfl_xor_sync(0xffffffffu, b[0], 16);
-          if (lane < 16) { atomicAdd(&s_stat[ch * 16 + lane], ts); atomicAdd(&s_stat[CB + ch * 16 + lane], tq); }
+          // lanes l and l ^ 16 hold the two halves of column (l & 15): the lower lane merges and stores
+          const float np_ = __shfl_xor_sync(0xffffffffu, nn, 16), pm = __shfl_xor_sync(0xffffffffu, a[0], 16), pq = __shfl_xor_sync(0xffffffffu, b[0], 16);
+          float m_ = a[0], q_ = b[0];
+          stat_merge<float>(nn, m_, q_, np_, pm, pq);
+          if (lane < 16) *reinterpret_cast<float4*>(pout + ch * 16 + lane) = make_float4(nn, m_, q_, 0.f);
         }
       }
     } else if (lane < 16) {
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
-        if (ch < nch) { atomicAdd(&s_stat[ch * 16 + lane], rs[ch]); atomicAdd(&s_stat[CB + ch * 16 + lane], rq[ch]); }
+        if (ch < nch) *reinterpret_cast<float4*>(pout + ch * 16 + lane) = make_float4(cnt, rs[ch], rq[ch], 0.f);
     }
     }   // !TCONV
   }
@@ -966,14 +1005,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
   tc::tc_fence_before();
   __syncthreads();
-  if constexpr (!TCONV) {
-    if (!idle)
-      for (int i = threadIdx.x - g * TPG; i < 2 * (int)CB; i += TPG) {      // each group flushes its own tile's sums
-        const int c = i % (int)CB, which = i / (int)CB;
-        atomicAdd(p.sums + ((size_t)n * p.Cout + (size_t)cb * CB + c) * 2 + which, (double)s_stat[i]);
-      }
-  }
-  if (p.cluster > 1) tc::cluster_sync();          // no CTA of a pair leaves while its peer may still signal it
   if (warp_abs == 1) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -1166,7 +1197,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   kp.tilesH = (kp.H + TC_TH - 1) / TC_TH; kp.tilesW = (kp.W + TC_TW - 1) / TC_TW;
   kp.ncb = cout / CB; kp.SA = SA; kp.NB = NB; kp.resident = resident; kp.G = G;
   kp.xf_src = nullptr;
-  kp.xform = 0; kp.xf_sums = nullptr; kp.xf_gamma = nullptr; kp.xf_beta = nullptr; kp.xf_inv_count = 0.f;
+  kp.xform = 0; kp.xf_sums = nullptr; kp.xf_gamma = nullptr; kp.xf_beta = nullptr; kp.xf_inv_count = 0.0;
   t.xform_ok = !strided && resident && c1 == 0 && KC == 32 && (cin == 32 || cin == 64) && CB <= 32 && SA >= 3;
   kp.R = std::min(TC_MAX_R, (512 / G) / CB);
   kp.fmt = bf16 ? 1 : 0;
@@ -1345,36 +1376,37 @@ inline int tc_set_attr_all() {
 
 inline int tc_init_attributes(bool bf16) { return bf16 ? tc_set_attr_all<__nv_bfloat16>() : tc_set_attr_all<__half>(); }
 
-// plain launch, or a launch in thread-block clusters of `cluster` CTAs along x (weight multicast)
-template <typename Kern>
-inline void tc_do_launch(Kern kern, unsigned grid, unsigned threads, size_t smem, cudaStream_t st, int cluster,
-                         const CUtensorMap& tm0, const CUtensorMap& tm1, const TcKParams& kp) {
-  if (cluster > 1) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid, 1, 1); cfg.blockDim = dim3(threads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kern, tm0, tm1, kp);
-  } else kern<<<grid, threads, smem, st>>>(tm0, tm1, kp);
-}
-
-struct TcXform { const double* sums; const float* gamma; const float* beta; float inv_count; const void* src; };
+struct TcXform { const double* sums; const float* gamma; const float* beta; double inv_count; const void* src; };
 struct TcFirstSrc { const float* src; const SampleMeta* metas; int patch_mode, SY, SZ; };
 
+// planes per z-block: split D until the grid fills the machine about twice
+inline int tc_plan_zb(const TcKParams& kp, int nb, int num_sms) {
+  const int tiles = kp.tilesH * kp.tilesW;
+  int ZB = kp.D;
+  while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 2) ZB = (ZB + 1) / 2;
+  return ZB;
+}
+
+// StatPartial entries one launch of this layer writes (0 for a transposed conv): [item][4 epilogue warps][CB]
+inline size_t tc_partials_needed(const TcKParams& kp, int nb, int num_sms) {
+  if (kp.tconv) return 0;
+  const int ZB = tc_plan_zb(kp, nb, num_sms);
+  return (size_t)nb * kp.ncb * ((kp.D + ZB - 1) / ZB) * kp.tilesH * kp.tilesW * 4 * kp.CB;
+}
+
+// sums: the layer's [n][Cout][2] fp64 statistics ({mean, variance} on return); partials: scratch of tc_partials_needed() entries
 template <typename T>
-int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, std::string* err, const TcXform* xf = nullptr, const TcFirstSrc* fs = nullptr) {
+int tc_launch(TcLayer& t, int nb, double* sums, StatPartial* partials, int num_sms, cudaStream_t st, std::string* err, const TcXform* xf = nullptr, const TcFirstSrc* fs = nullptr) {
   TcKParams kp = t.kp;
-  kp.sums = sums;
+  kp.partials = partials;
+  if (!kp.tconv && (!sums || !partials)) { if (err) *err = "conv launch without a statistics buffer"; return 1; }
   if (kp.first) {
     if (!fs) { if (err) *err = "first-conv launch without a source"; return 1; }
     kp.fc_src = fs->src; kp.fc_metas = fs->metas; kp.fc_patch_mode = fs->patch_mode; kp.fc_SY = fs->SY; kp.fc_SZ = fs->SZ;
   }
   if (xf && t.xform_ok) { kp.xform = 1; kp.xf_sums = xf->sums; kp.xf_gamma = xf->gamma; kp.xf_beta = xf->beta; kp.xf_inv_count = xf->inv_count; kp.xf_src = xf->src; }
   const int tiles = kp.tilesH * kp.tilesW;
-  int ZB = kp.D;
-  while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 2) ZB = (ZB + 1) / 2;
+  const int ZB = tc_plan_zb(kp, nb, num_sms);
   kp.ZB = ZB; kp.nzb = (kp.D + ZB - 1) / ZB;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DWMH_TC_DEBUG"); dbg = e ? atoi(e) : 0; } kp.dbg = dbg; }
   const long long items = (long long)nb * kp.ncb * kp.nzb * tiles;
@@ -1382,17 +1414,6 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   // one (n, cb) when the tiles x z-blocks count is even
   if (!kp.first && kp.G == 2 && (kp.resident ? ((long long)kp.nzb * tiles) % 2 != 0 : tiles % 2 != 0)) kp.G = 1;    // (streamed weights: same z-block too)
   kp.total_items = (int)items;
-  // CTA pairs (clusters of 2) for streamed weights: both CTAs must walk the same tile sequence -> same (n, cout block, z-block)
-  {
-    // opt-in (DWMH_TC_CLUSTER=1; read per launch so that a test can toggle it): measured neutral on the benchmark -- the
-    // streamed layers are not bound by L2 weight traffic ("What did not work")
-    const char* e = getenv("DWMH_TC_CLUSTER");
-    const int allow_cluster = e ? atoi(e) : 0;
-    kp.mcast = allow_cluster == 1;
-    kp.cluster = (allow_cluster && !kp.resident && !kp.tconv && !kp.first && !kp.xform && tiles % (2 * kp.G) == 0) ? 2 : 1;
-  }
-  const int launch_cluster = kp.cluster;
-  { const char* e = getenv("DWMH_TC_CLUSTER"); if (e && atoi(e) == 3) kp.cluster = 1; }      // debug: cluster launch, cluster code off
   const unsigned grid = (unsigned)((items + kp.G - 1) / kp.G);
   const unsigned threads = TC_THREADS * kp.G;
   static unsigned long long* prof_dev = nullptr;
@@ -1403,7 +1424,7 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
   kp.prof = prof_dev;
   const int ks = kp.KC / 16;
   const bool small = kp.CB <= 32 && !kp.tconv;
-#define DWMH_TC_LAUNCH(K, S, C, D) tc_do_launch(conv3_tc_kernel<T, K, S, C, D, false>, grid, threads, t.smem_bytes, st, launch_cluster, t.tm0, t.tm1, kp)
+#define DWMH_TC_LAUNCH(K, S, C, D) conv3_tc_kernel<T, K, S, C, D, false><<<grid, threads, t.smem_bytes, st>>>(t.tm0, t.tm1, kp)
 #define DWMH_TC_LAUNCH_K(S, C, D) do { if (ks == 1) DWMH_TC_LAUNCH(1, S, C, D); else if (ks == 2) DWMH_TC_LAUNCH(2, S, C, D); else DWMH_TC_LAUNCH(4, S, C, D); } while (0)
   if (kp.first) conv3_tc_kernel<T, 2, true, false, true, false, true><<<grid, 512, t.smem_bytes, st>>>(t.tm0, t.tm1, kp);
   else if (kp.xform) {
@@ -1417,6 +1438,12 @@ int tc_launch(TcLayer& t, int nb, double* sums, int num_sms, cudaStream_t st, st
 #undef DWMH_TC_LAUNCH
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { if (err) *err = std::string("conv3_tc_kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+  if (!kp.tconv) {
+    const int jn = std::max(1, 256 / kp.CB);
+    stats_reduce_kernel<<<nb * kp.ncb, kp.CB * jn, 0, st>>>(partials, sums, kp.ncb, kp.CB, kp.Cout, kp.nzb * tiles, jn);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { if (err) *err = std::string("stats_reduce_kernel launch failed: ") + cudaGetErrorString(e); return 1; }
+  }
   if (kp.dbg & 8) {
     unsigned long long h[16];
     cudaStreamSynchronize(st);

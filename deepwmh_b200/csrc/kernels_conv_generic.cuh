@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(128) conv_generic_kernel(ConvParams p) {
 struct S2dParams { void* dst; int D, H, W, sd, sh, sw; };
 
 template <typename T>
-__global__ void __launch_bounds__(256) instnorm_lrelu_kernel(const void* __restrict__ raw, int raw32, void* __restrict__ y, NormParams np,
+// raw and y alias when the layer is normalised in place (fp16 raw storage): no __restrict__ on either.
+__global__ void __launch_bounds__(256) instnorm_lrelu_kernel(const void* raw, int raw32, void* y, NormParams np,
                                                              int C, int64_t V, S2dParams sp) {
   __shared__ float sa[8], sb[8];
   const int n = blockIdx.y / (C >> 3), cc = blockIdx.y % (C >> 3);

@@ -183,8 +183,10 @@ __global__ void __launch_bounds__(256) aggregate_tile_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------
 // a12 tail: class_probabilities = agg / wgt; seg = argmax (first maximum).  21 B/voxel.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ agg, const float* __restrict__ wgt,
-                                                       float* __restrict__ softmax_out, uint8_t* __restrict__ seg,
+// softmax_out may alias agg (in-place normalisation): neither is __restrict__ and every thread reads its own
+// elements before it writes them.
+__global__ void __launch_bounds__(256) finalize_kernel(const float* agg, const float* __restrict__ wgt,
+                                                       float* softmax_out, uint8_t* __restrict__ seg,
                                                        int64_t V) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += stride) {

@@ -36,6 +36,18 @@ int fail(const char* fmt, ...) {
 #define S1_CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) \
   return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); } while (0)
 
+// Entry points run on `device` and leave the caller's current device as they found it.
+struct S1DevGuard {
+  int prev = -1; bool ok = false;
+  explicit S1DevGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    if (prev == dev) prev = -1;
+  }
+  ~S1DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define S1_DEV(dev) S1DevGuard dev_guard__(dev); if (!dev_guard__.ok) return fail("cudaSetDevice(%d) failed", (int)(dev))
+
 int grid_for(int device) {
   static int sms[64] = {0};
   if (device < 0 || device >= 64) return 148 * 8;
@@ -726,7 +738,7 @@ extern "C" int dwmh_s1_zscore(int32_t device, float* x, const float* mask, int64
   if (n <= 0) return fail("dwmh_s1_zscore: empty volume");
   if (fill_outside && !mask) return fail("dwmh_s1_zscore: fill_outside needs a mask");
   cudaStream_t st = (cudaStream_t)stream_;
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   VolPtrs vols{}; vols.p[0] = x;
   if (zscore_launch(device, vols, 1, mask, n, fill_outside, workspace, (((uintptr_t)x | (uintptr_t)mask) & 15) == 0, st)) return 1;
   if (stats_out) {
@@ -749,7 +761,7 @@ extern "C" int dwmh_s1_zscore_batch(int32_t device, float* const* xs, int32_t nv
   VolPtrs vols{};
   uintptr_t al = (uintptr_t)mask;
   for (int i = 0; i < nvol; ++i) { if (!xs[i]) return fail("dwmh_s1_zscore_batch: xs[%d] is null", i); vols.p[i] = xs[i]; al |= (uintptr_t)xs[i]; }
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   return zscore_launch(device, vols, nvol, mask, n, fill_outside, workspace, (al & 15) == 0, (cudaStream_t)stream_);
 }
 
@@ -768,7 +780,7 @@ extern "C" int dwmh_s1_mean_std_grid(int32_t device, const float* x, const float
   GridGeom q;
   if (geom(X, Y, Z, patch_size, &q)) return 1;
   cudaStream_t st = (cudaStream_t)stream_;
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   const size_t ncell = (size_t)q.g[0] * q.g[1] * q.g[2], ngrid = (size_t)(q.g[0] + 2) * (q.g[1] + 2) * (q.g[2] + 2);
   double* cells = (double*)workspace;
   double* mg = (double*)((char*)workspace + align256(ncell * 3 * sizeof(double)));
@@ -807,7 +819,7 @@ extern "C" int dwmh_s1_local_mean_align(int32_t device, const float* target, flo
   VolPtrs vols{}; vols.p[0] = const_cast<float*>(target);
   for (int i = 0; i < k; ++i) { if (!refs[i]) return fail("dwmh_s1_local_mean_align: refs[%d] is null", i); vols.p[i + 1] = refs[i]; }
   cudaStream_t st = (cudaStream_t)stream_;
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   const int nvol = k + 1;
   const size_t ncell = (size_t)q.g[0] * q.g[1] * q.g[2], gstride = align256((size_t)(q.g[0] + 2) * (q.g[1] + 2) * (q.g[2] + 2) * sizeof(double)) / sizeof(double);
   const size_t cells_bytes = align256((size_t)nvol * ncell * 3 * sizeof(double));
@@ -827,7 +839,7 @@ extern "C" int dwmh_s1_local_mean_align(int32_t device, const float* target, flo
 
 extern "C" int dwmh_s1_align_local_mean(int32_t device, float* x, const float* local_mu, const float* target_local_mu, int64_t n, void* stream_) {
   if (!x || !local_mu || !target_local_mu) return fail("dwmh_s1_align_local_mean: null argument");
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   s1_align_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x, local_mu, target_local_mu, n);
   S1_CU(cudaGetLastError());
   return 0;
@@ -845,7 +857,7 @@ static int group_nll_impl(const char* who, int32_t device, const float* x_prime,
     rp.p[i] = refs[i];
     if (masks) mp.p[i] = masks[i];
   }
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   const NllParams q{min_std, side, k};
   cudaStream_t st = (cudaStream_t)stream_;
   if (masks) {
@@ -879,7 +891,7 @@ extern "C" int dwmh_s1_median_filter(int32_t device, const float* in, float* out
   if (X <= 0 || Y <= 0 || Z <= 0) return fail("dwmh_s1_median_filter: empty volume");
   const int kx = kernel_size[0], ky = kernel_size[1], kz = kernel_size[2];
   if (kx < 1 || ky < 1 || kz < 1 || kx > 9 || ky > 9 || kz > 9) return fail("dwmh_s1_median_filter: kernel %dx%dx%d (1..9 per axis supported)", kx, ky, kz);
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   const size_t smem = (size_t)(MT_X + kx - 1) * (MT_Y + ky - 1) * (MT_Z + kz - 1) * sizeof(uint32_t);
   dim3 grid((Z + MT_Z - 1) / MT_Z, (Y + MT_Y - 1) / MT_Y, (X + MT_X - 1) / MT_X);
   if (grid.y > 65535 || grid.z > 65535) return fail("dwmh_s1_median_filter: volume too large");
@@ -918,7 +930,7 @@ extern "C" int dwmh_s1_component_filtering(int32_t device, const float* mask, in
     for (int a = 0; a < 3; ++a) filt[a] = a == am;
   }
   cudaStream_t st = (cudaStream_t)stream_;
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   int* L = (int*)workspace;
   int* size = (int*)((char*)workspace + align256((size_t)V * 4));
   float* acc = (float*)((char*)workspace + 2 * align256((size_t)V * 4));
@@ -944,7 +956,7 @@ extern "C" int dwmh_s1_minmax(int32_t device, const float* x, const float* mask,
   if (!x || !workspace || !out_minmax) return fail("dwmh_s1_minmax: null argument");
   if (n <= 0) return fail("dwmh_s1_minmax: empty volume");
   cudaStream_t st = (cudaStream_t)stream_;
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   const int init[2] = {0x7fffffff, (int)0x80000000};
   int* mm = (int*)workspace;
   S1_CU(cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, st));
@@ -964,7 +976,7 @@ extern "C" int dwmh_s1_histogram(int32_t device, const float* x, const float* ma
   if (n <= 0) return fail("dwmh_s1_histogram: empty volume");
   if (nbins < 1 || nbins > 2048) return fail("dwmh_s1_histogram: nbins = %d (1..2048 supported)", nbins);
   cudaStream_t st = (cudaStream_t)stream_;
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   S1_CU(cudaMemsetAsync(counts, 0, (size_t)nbins * sizeof(uint64_t), st));
   const size_t smem = (size_t)(nbins + 1) * sizeof(double) + (size_t)nbins * sizeof(unsigned int);
   s1_histogram_kernel<<<grid_for(device) / 2, 256, smem, st>>>(x, mask, n, fill_outside, fill_value, edges, nbins,
@@ -975,7 +987,7 @@ extern "C" int dwmh_s1_histogram(int32_t device, const float* x, const float* ma
 
 extern "C" int dwmh_s1_threshold_mask(int32_t device, const float* x, float threshold, const float* mul_mask, float* out, int64_t n, void* stream_) {
   if (!x || !out) return fail("dwmh_s1_threshold_mask: null argument");
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   s1_threshold_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(x, threshold, mul_mask, out, n);
   S1_CU(cudaGetLastError());
   return 0;
@@ -990,7 +1002,7 @@ extern "C" int dwmh_s1_masked_sums(int32_t device, const float* const* xs, int32
   uintptr_t al = (uintptr_t)mask;
   for (int i = 0; i < nvol; ++i) { if (!xs[i]) return fail("dwmh_s1_masked_sums: xs[%d] is null", i); vols.p[i] = const_cast<float*>(xs[i]); al |= (uintptr_t)xs[i]; }
   cudaStream_t st = (cudaStream_t)stream_;
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   double* ws = (double*)workspace;
   S1_CU(cudaMemsetAsync(ws, 0, (size_t)nvol * ZS_SLOT * sizeof(double), st));
   S1_CU(cudaMemset2DAsync((char*)workspace + 32, ZS_SLOT * sizeof(double), 0x7f, 4, nvol, st));
@@ -1012,7 +1024,7 @@ extern "C" int dwmh_s1_label_vote(int32_t device, const float* const* labels, in
   if (num_labels < 1 || num_labels > S1_MAX_LABELS) return fail("dwmh_s1_label_vote: %d label ids (1..%d supported)", num_labels, S1_MAX_LABELS);
   RefPtrs rp{};
   for (int i = 0; i < k; ++i) { if (!labels[i]) return fail("dwmh_s1_label_vote: labels[%d] is null", i); rp.p[i] = labels[i]; }
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   s1_label_vote_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(rp, k, num_labels, averaged_label, tissue_majority, n);
   S1_CU(cudaGetLastError());
   return 0;
@@ -1023,7 +1035,7 @@ extern "C" int dwmh_s1_apply_priors(int32_t device, float* anomaly, const float*
   if (!anomaly || !averaged_label) return fail("dwmh_s1_apply_priors: null argument");
   if (stage != 1 && stage != 2) return fail("dwmh_s1_apply_priors: stage must be 1 or 2");
   if (stage == 2 && (!anomaly_median || !tissue_majority)) return fail("dwmh_s1_apply_priors: stage 2 needs the median-filtered score and the tissue mask");
-  S1_CU(cudaSetDevice(device));
+  S1_DEV(device);
   s1_apply_priors_kernel<<<grid_for(device), 256, 0, (cudaStream_t)stream_>>>(anomaly, anomaly_median, averaged_label, tissue_majority, stage, n);
   S1_CU(cudaGetLastError());
   return 0;

@@ -58,7 +58,7 @@ def mirror_axes_mask(mirror_axes: Sequence[int]) -> int:
 class SegmentationNetwork:
     """The `trainer.network` object: Generic_UNet weights resident on one B200 + predict_3D."""
 
-    def __init__(self, plans: Dict, device: int = 0, act_dtype: str = "fp16", max_batch: int = 8, lanes: int = 0):
+    def __init__(self, plans: Dict, device: int = 0, act_dtype: str = "fp16", max_batch: int = 8):
         if not torch.cuda.is_available():
             raise _lib.DwmhError("deepwmh_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
         self._lib = _lib.load()
@@ -88,7 +88,7 @@ class SegmentationNetwork:
                 d.conv_kernel_sizes[i][a] = k[a]
         d.act_dtype = ACT_DTYPES[act_dtype]
         d.max_batch = int(max_batch)
-        d.lanes = int(lanes)
+        d.struct_size = C.sizeof(NetDesc)
         self._desc = d
         self._ctx = C.c_void_p()
         check(self._lib.dwmh_create(C.byref(self._ctx), device, C.byref(d)))
@@ -276,11 +276,11 @@ class nnUNetTrainerV2:
     """The slice of the trainer surface `predict_cases` uses [U:nnUNetTrainerV2.py], B200-backed."""
 
     def __init__(self, plans: Dict, device: int = 0, act_dtype: str = "fp16", max_batch: int = 8,
-                 exact_scipy_gaussian: bool = True, lanes: int = 0):
+                 exact_scipy_gaussian: bool = True):
         self.plans = plans
         self.process_plans(plans)
         self.data_aug_params = {"do_mirror": True, "mirror_axes": (0, 1, 2)}
-        self.network = SegmentationNetwork(plans, device, act_dtype, max_batch, lanes)
+        self.network = SegmentationNetwork(plans, device, act_dtype, max_batch)
         if exact_scipy_gaussian:
             self.network.install_scipy_gaussian()
 

@@ -40,9 +40,10 @@ typedef struct dwmh_net_desc {
   int32_t pool_op_kernel_sizes[DWMH_MAX_POOL][3];      /* each entry 1 or 2                          */
   int32_t conv_kernel_sizes[DWMH_MAX_POOL + 1][3];     /* each entry 1 or 3                          */
   int32_t act_dtype;                          /* 0 = fp16 operands/storage (default), 1 = bf16       */
-  int32_t max_batch;                          /* patch forwards per lane batch (multiple of 8), 0 = default 8 */
-  int32_t lanes;                              /* independent forward pipelines on separate streams, 0 = default 1
-                                               * (measured on B200: kernels of different lanes do not co-run, so >1 buys nothing yet) */
+  int32_t max_batch;                          /* patch forwards per batch (multiple of the mirror count), 0 = default 8 */
+  int32_t struct_size;                        /* MUST be sizeof(dwmh_net_desc): dwmh_create rejects any other value, so a
+                                               * binding built against another layout of this struct fails loudly instead
+                                               * of being read past its end                                           */
 } dwmh_net_desc;
 
 const char* dwmh_last_error(void);
