@@ -29,6 +29,7 @@ SYMBOLS = {
     "dwmh_version": (C.c_int, []),
     "dwmh_create": (C.c_int, [C.POINTER(_P), C.c_int, C.POINTER(NetDesc)]),
     "dwmh_destroy": (C.c_int, [_P]),
+    "dwmh_create_like": (C.c_int, [C.POINTER(_P), _P]),
     "dwmh_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int32]),
     "dwmh_commit_weights": (C.c_int, [_P]),
     "dwmh_zscore": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_double), _P]),
@@ -38,6 +39,7 @@ SYMBOLS = {
     "dwmh_set_importance_map": (C.c_int, [_P, _P]),
     "dwmh_predict_3d": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32,
                                   _P, _P, C.c_int32, C.c_int32, _P]),
+    "dwmh_weight_map": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, _P]),
     "dwmh_finalize": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "dwmh_axpy": (C.c_int, [_P, _P, _P, C.c_float, C.c_int64, _P]),
     "dwmh_argmax2": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
@@ -66,6 +68,8 @@ SYMBOLS = {
     "dwmh_s1_apply_priors": (C.c_int, [C.c_int32, _P, _P, _P, _P, C.c_int32, C.c_int64, _P]),
     "dwmh_predict_volume_host": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
                                            C.c_int32, C.c_int32, _P, _P, _P]),
+    "dwmh_predict_volume_host_masked": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                                  C.c_int32, C.c_int32, _P, _P, _P]),
     "dwmh_forward_patches": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     "dwmh_debug_layer_output": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int32), _P]),
     "dwmh_num_layers": (C.c_int, [_P]),

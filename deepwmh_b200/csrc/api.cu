@@ -106,6 +106,7 @@ struct dwmh_ctx {
   StatPartial* stat_partials = nullptr; size_t stat_partials_cap = 0;   // per-CTA Welford partials of the layer in flight
   float* probs = nullptr;            // [maxN][2][P]
   bool buffers_ready = false;
+  dwmh_ctx* lender = nullptr;        // dwmh_create_like: activation workspaces are borrowed from this context
   float* gauss_dev = nullptr; std::vector<float> gauss_host; bool gauss_custom = false;
   SampleMeta* metas_dev = nullptr; size_t metas_cap = 0;
   double* zs_acc = nullptr;
@@ -217,6 +218,18 @@ extern "C" int dwmh_create(dwmh_ctx** out, int device, const dwmh_net_desc* desc
   return 0;
 }
 
+extern "C" int dwmh_create_like(dwmh_ctx** out, dwmh_ctx* parent) {
+  if (!out || !parent) return fail("dwmh_create_like: null argument");
+  if (parent->lender) return fail("dwmh_create_like: the parent itself borrows its workspaces; pass the owning context");
+  if (!parent->buffers_ready) return fail("dwmh_create_like: commit the parent's weights first (its workspaces do not exist yet)");
+  dwmh_ctx* c = nullptr;
+  DW_TRY(dwmh_create(&c, parent->device, &parent->d));
+  c->max_batch = parent->max_batch; c->raw32_max_edge = parent->raw32_max_edge;
+  c->lender = parent;
+  *out = c;
+  return 0;
+}
+
 static void free_dev(void* p) { if (p) cudaFree(p); }
 
 extern "C" int dwmh_destroy(dwmh_ctx* c) {
@@ -224,11 +237,10 @@ extern "C" int dwmh_destroy(dwmh_ctx* c) {
   DevGuard dg(c->device);
   cudaDeviceSynchronize();
   for (auto& L : c->layers) {
-    if (L.raw != L.out) free_dev(L.raw);
-    free_dev(L.out); free_dev(L.s2d);
+    if (!c->lender) { if (L.raw != L.out) free_dev(L.raw); free_dev(L.out); free_dev(L.s2d); }
     free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc);
   }
-  free_dev(c->stats_arena); free_dev(c->probs); free_dev(c->stat_partials);
+  if (!c->lender) { free_dev(c->stats_arena); free_dev(c->probs); free_dev(c->stat_partials); }
   free_dev(c->w_head_dev); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
   free_dev(c->hv_vol); free_dev(c->hv_pad); free_dev(c->hv_agg); free_dev(c->hv_wgt); free_dev(c->hv_seg);
   free_dev(c->ccl_labels); free_dev(c->ccl_sizes);
@@ -357,6 +369,17 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
   size_t stat_doubles = 0;
   for (auto& L : c->layers) if (L.has_norm) stat_doubles += (size_t)maxN * L.cout * 2;
   c->stats_bytes = stat_doubles * sizeof(double);
+  if (!c->buffers_ready && c->lender) {
+    dwmh_ctx* o = c->lender;
+    if (o->layers.size() != c->layers.size() || o->max_batch != maxN) return fail("dwmh_commit_weights: lender context does not match");
+    c->stats_arena = o->stats_arena; c->probs = o->probs;
+    for (int i = 0; i < nL; ++i) {
+      Layer& L = c->layers[i]; const Layer& S = o->layers[i];
+      if (L.raw32 != S.raw32) return fail("dwmh_commit_weights: lender context does not match (raw storage of %s)", L.name.c_str());
+      L.sums = S.sums; L.out = S.out; L.raw = S.raw; L.s2d = S.s2d;
+    }
+    c->buffers_ready = true;
+  }
   if (!c->buffers_ready) {
     CU_TRY(cudaMalloc((void**)&c->stats_arena, c->stats_bytes));
     CU_TRY(cudaMalloc((void**)&c->probs, (size_t)maxN * 2 * c->P() * sizeof(float)));
@@ -404,7 +427,10 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
     for (auto& L : c->layers)
       if (L.tc.enabled)
         for (int nb = 1; nb <= maxN; ++nb) need = std::max(need, tc_partials_needed(L.tc.kp, nb, c->num_sms));
-    if (need > c->stat_partials_cap) {
+    if (c->lender) {
+      if (need > c->lender->stat_partials_cap) return fail("dwmh_commit_weights: lender's statistics scratch is too small");
+      c->stat_partials = c->lender->stat_partials; c->stat_partials_cap = c->lender->stat_partials_cap;
+    } else if (need > c->stat_partials_cap) {
       free_dev(c->stat_partials); c->stat_partials = nullptr; c->stat_partials_cap = 0;
       CU_TRY(cudaMalloc((void**)&c->stat_partials, need * sizeof(StatPartial)));
       c->stat_partials_cap = need;
@@ -745,6 +771,29 @@ extern "C" int dwmh_predict_3d(dwmh_ctx* c, const float* vol, int32_t X, int32_t
   return 0;
 }
 
+extern "C" int dwmh_weight_map(dwmh_ctx* c, int32_t X, int32_t Y, int32_t Z, double step_size, int32_t use_gaussian, float* wgt, void* stream_) {
+  if (!c || !wgt) return fail("dwmh_weight_map: null argument");
+  if (!c->gauss_dev) return fail("dwmh_weight_map: weights not committed (no importance map yet)");
+  DEV_GUARD(c->device);
+  const int32_t* ps = c->d.patch_size;
+  const int img[3] = {X, Y, Z};
+  TileSteps ts;
+  int ntiles = 1;
+  for (int a = 0; a < 3; ++a) {
+    std::vector<int> s_;
+    DW_TRY(steps_1d(ps[a], img[a], step_size, s_));
+    if ((int)s_.size() > WM_MAX_STEPS) return fail("dwmh_weight_map: more than %d tiles along axis %d", WM_MAX_STEPS, a);
+    ts.n[a] = (int)s_.size();
+    for (size_t i = 0; i < s_.size(); ++i) ts.s[a][i] = s_[i];
+    ntiles *= (int)s_.size();
+  }
+  const bool gauss = use_gaussian && ntiles > 1;
+  weight_map_kernel<<<c->num_sms * 8, 256, 0, (cudaStream_t)stream_>>>(gauss ? c->gauss_dev : nullptr, wgt, ts, ps[0], ps[1], ps[2], X, Y, Z);
+  c->launches++;
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int dwmh_finalize(dwmh_ctx* c, const float* agg, const float* wgt, float* softmax, uint8_t* seg,
                              int32_t X, int32_t Y, int32_t Z, void* stream_) {
   if (!c || !agg || !wgt) return fail("dwmh_finalize: null argument");
@@ -828,12 +877,33 @@ extern "C" int dwmh_remove_sparks(dwmh_ctx* c, const uint8_t* seg, int32_t X, in
   return 0;
 }
 
+static int predict_volume_host_impl(dwmh_ctx* c, const float* vol_host, const int8_t* seg_mask_host, int32_t X, int32_t Y, int32_t Z,
+                                    int32_t zscore_mask_mode, double step_size, int32_t do_mirroring,
+                                    int32_t mirror_axes_mask, int32_t use_gaussian,
+                                    float* softmax_host, uint8_t* seg_host, void* stream_);
+
 extern "C" int dwmh_predict_volume_host(dwmh_ctx* c, const float* vol_host, int32_t X, int32_t Y, int32_t Z,
                                         int32_t zscore_mask_mode, double step_size, int32_t do_mirroring,
                                         int32_t mirror_axes_mask, int32_t use_gaussian,
                                         float* softmax_host, uint8_t* seg_host, void* stream_) {
+  if (zscore_mask_mode == 1) return fail("dwmh_predict_volume_host: mask_mode 1 needs the crop mask; use dwmh_predict_volume_host_masked");
+  return predict_volume_host_impl(c, vol_host, nullptr, X, Y, Z, zscore_mask_mode, step_size, do_mirroring, mirror_axes_mask, use_gaussian,
+                                  softmax_host, seg_host, stream_);
+}
+
+extern "C" int dwmh_predict_volume_host_masked(dwmh_ctx* c, const float* vol_host, const int8_t* seg_mask_host, int32_t X, int32_t Y, int32_t Z,
+                                               double step_size, int32_t do_mirroring, int32_t mirror_axes_mask, int32_t use_gaussian,
+                                               float* softmax_host, uint8_t* seg_host, void* stream_) {
+  if (!seg_mask_host) return fail("dwmh_predict_volume_host_masked: null crop mask");
+  return predict_volume_host_impl(c, vol_host, seg_mask_host, X, Y, Z, 1, step_size, do_mirroring, mirror_axes_mask, use_gaussian,
+                                  softmax_host, seg_host, stream_);
+}
+
+static int predict_volume_host_impl(dwmh_ctx* c, const float* vol_host, const int8_t* seg_mask_host, int32_t X, int32_t Y, int32_t Z,
+                                    int32_t zscore_mask_mode, double step_size, int32_t do_mirroring,
+                                    int32_t mirror_axes_mask, int32_t use_gaussian,
+                                    float* softmax_host, uint8_t* seg_host, void* stream_) {
   if (!c || !vol_host) return fail("dwmh_predict_volume_host: null argument");
-  if (zscore_mask_mode == 1) return fail("dwmh_predict_volume_host: mask_mode 1 needs a device seg; use dwmh_zscore");
   cudaStream_t st = (cudaStream_t)stream_;
   DEV_GUARD(c->device);
   const int64_t V = (int64_t)X * Y * Z;
@@ -848,7 +918,13 @@ extern "C" int dwmh_predict_volume_host(dwmh_ctx* c, const float* vol_host, int3
   DW_TRY(grow(&c->hv_wgt, &c->hv_wgt_cap, (size_t)PV));
   DW_TRY(grow(&c->hv_seg, &c->hv_seg_cap, (size_t)PV));
   CU_TRY(cudaMemcpyAsync(c->hv_vol, vol_host, V * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (zscore_mask_mode >= 0) DW_TRY(dwmh_zscore(c, c->hv_vol, nullptr, V, zscore_mask_mode, nullptr, st));
+  const int8_t* mask_dev = nullptr;
+  if (seg_mask_host) {
+    // the crop mask rides in the (not yet used) label buffer: 1 byte per voxel, 4-byte aligned
+    CU_TRY(cudaMemcpyAsync(c->hv_seg, seg_mask_host, V, cudaMemcpyHostToDevice, st));
+    mask_dev = reinterpret_cast<const int8_t*>(c->hv_seg);
+  }
+  if (zscore_mask_mode >= 0) DW_TRY(dwmh_zscore(c, c->hv_vol, mask_dev, V, zscore_mask_mode, nullptr, st));
   const float* vol_dev = c->hv_vol;
   if (padded) {
     DW_TRY(grow(&c->hv_pad, &c->hv_pad_cap, (size_t)PV));

@@ -181,6 +181,38 @@ __global__ void __launch_bounds__(256) aggregate_tile_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// a12, tile-sharded mode: the weight buffer is data-independent, so a rank computes ALL of it locally instead of
+// reducing it over NVLink.  Per voxel the importance map of every covering tile is added in tile order (x outer, z
+// inner) -- the fp32 sequence the per-tile overlap-add of a single-GPU run performs, hence bit-identical to it.
+// ---------------------------------------------------------------------------------------------
+constexpr int WM_MAX_STEPS = 64;
+struct TileSteps { int n[3]; int s[3][WM_MAX_STEPS]; };
+
+__global__ void __launch_bounds__(256) weight_map_kernel(const float* __restrict__ gauss, float* __restrict__ wgt, TileSteps ts,
+                                                         int px, int py, int pz, int X, int Y, int Z) {
+  const int64_t V = (int64_t)X * Y * Z;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride) {
+    const int z = (int)(v % Z), y = (int)((v / Z) % Y), x = (int)(v / ((int64_t)Z * Y));
+    float w = 0.f;
+    for (int ix = 0; ix < ts.n[0]; ++ix) {
+      const int i = x - ts.s[0][ix];
+      if ((unsigned)i >= (unsigned)px) continue;
+      for (int iy = 0; iy < ts.n[1]; ++iy) {
+        const int j = y - ts.s[1][iy];
+        if ((unsigned)j >= (unsigned)py) continue;
+        for (int iz = 0; iz < ts.n[2]; ++iz) {
+          const int k = z - ts.s[2][iz];
+          if ((unsigned)k >= (unsigned)pz) continue;
+          w += gauss ? __ldg(gauss + ((int64_t)i * py + j) * pz + k) : 1.0f;
+        }
+      }
+    }
+    wgt[v] = w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // a12 tail: class_probabilities = agg / wgt; seg = argmax (first maximum).  21 B/voxel.
 // ---------------------------------------------------------------------------------------------
 // softmax_out may alias agg (in-place normalisation): neither is __restrict__ and every thread reads its own

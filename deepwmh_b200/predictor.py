@@ -29,8 +29,9 @@ def _ptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None) -> C.c_void_p:
+    """The caller's current stream ON `device` (a stream handle is only valid on its own device)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def pad_nd_image(image: np.ndarray, new_shape, mode="constant", kwargs=None):
@@ -58,7 +59,10 @@ def mirror_axes_mask(mirror_axes: Sequence[int]) -> int:
 class SegmentationNetwork:
     """The `trainer.network` object: Generic_UNet weights resident on one B200 + predict_3D."""
 
-    def __init__(self, plans: Dict, device: int = 0, act_dtype: str = "fp16", max_batch: int = 8):
+    def __init__(self, plans: Dict, device: int = 0, act_dtype: str = "fp16", max_batch: int = 8,
+                 share_workspace_with: "Optional[SegmentationNetwork]" = None):
+        """share_workspace_with: another network of the same plans on the same device whose activation buffers this one
+        borrows (k resident models of a checkpoint ensemble, dwmh_create_like); the lender must have its weights loaded."""
         if not torch.cuda.is_available():
             raise _lib.DwmhError("deepwmh_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
         self._lib = _lib.load()
@@ -91,7 +95,11 @@ class SegmentationNetwork:
         d.struct_size = C.sizeof(NetDesc)
         self._desc = d
         self._ctx = C.c_void_p()
-        check(self._lib.dwmh_create(C.byref(self._ctx), device, C.byref(d)))
+        self._lender = share_workspace_with          # keeps the lender alive
+        if share_workspace_with is not None:
+            check(self._lib.dwmh_create_like(C.byref(self._ctx), share_workspace_with._ctx))
+        else:
+            check(self._lib.dwmh_create(C.byref(self._ctx), device, C.byref(d)))
         self._weights_loaded = False
         self._gaussian_installed = False
 
@@ -137,12 +145,32 @@ class SegmentationNetwork:
         check(self._lib.dwmh_set_importance_map(self._ctx, g.ctypes.data_as(C.c_void_p)))
         self._gaussian_installed = True
 
+    def _st(self) -> C.c_void_p:
+        return _stream(self.device)
+
     # ---- device-level pieces (used by the sharded drivers) ---------------------------------------
+    def weight_map(self, shape: Sequence[int], step_size: float, use_gaussian: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """wgt [X,Y,Z] of the complete tile set (dwmh_weight_map): data-independent, computed locally by every rank."""
+        X, Y, Z = (int(v) for v in shape)
+        wgt = out if out is not None else torch.empty((X, Y, Z), dtype=torch.float32, device=self.device)
+        check(self._lib.dwmh_weight_map(self._ctx, X, Y, Z, float(step_size), int(bool(use_gaussian)), _ptr(wgt), self._st()))
+        return wgt
+
+    def axpy_(self, acc: torch.Tensor, x: torch.Tensor, alpha: float):
+        """acc += alpha * x on the device (a13: running mean of the k models' softmax)."""
+        assert acc.is_cuda and x.is_cuda and acc.dtype == x.dtype == torch.float32 and acc.is_contiguous() and x.is_contiguous()
+        check(self._lib.dwmh_axpy(self._ctx, _ptr(acc), _ptr(x), float(alpha), acc.numel(), self._st()))
+
+    def argmax2(self, softmax: torch.Tensor) -> torch.Tensor:
+        seg = torch.empty(tuple(softmax.shape[1:]), dtype=torch.uint8, device=softmax.device)
+        check(self._lib.dwmh_argmax2(self._ctx, _ptr(softmax), _ptr(seg), seg.numel(), self._st()))
+        return seg
+
     def normalize_(self, vol: torch.Tensor, seg: Optional[torch.Tensor] = None, mask_mode: int = 2):
         """In-place z-score of a device fp32 volume (a2).  mask_mode: 0 all, 1 seg>=0, 2 vol!=0."""
         assert vol.is_cuda and vol.dtype == torch.float32 and vol.is_contiguous()
         stats = (C.c_double * 3)()
-        check(self._lib.dwmh_zscore(self._ctx, _ptr(vol), _ptr(seg), vol.numel(), mask_mode, stats, _stream()))
+        check(self._lib.dwmh_zscore(self._ctx, _ptr(vol), _ptr(seg), vol.numel(), mask_mode, stats, self._st()))
         return tuple(stats)
 
     def accumulate_tiles(self, vol: torch.Tensor, agg: torch.Tensor, wgt: torch.Tensor, step_size: float,
@@ -152,12 +180,12 @@ class SegmentationNetwork:
         X, Y, Z = vol.shape
         check(self._lib.dwmh_predict_3d(self._ctx, _ptr(vol), X, Y, Z, float(step_size), int(bool(do_mirroring)),
                                         mirror_axes_mask(mirror_axes), int(bool(use_gaussian)), _ptr(agg), _ptr(wgt),
-                                        int(tile_begin), int(tile_end), _stream()))
+                                        int(tile_begin), int(tile_end), self._st()))
 
     def finalize(self, agg: torch.Tensor, wgt: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         X, Y, Z = wgt.shape
         seg = torch.empty((X, Y, Z), dtype=torch.uint8, device=agg.device)
-        check(self._lib.dwmh_finalize(self._ctx, _ptr(agg), _ptr(wgt), _ptr(agg), _ptr(seg), X, Y, Z, _stream()))
+        check(self._lib.dwmh_finalize(self._ctx, _ptr(agg), _ptr(wgt), _ptr(agg), _ptr(seg), X, Y, Z, self._st()))
         return seg, agg
 
     def ensemble_masked_add_(self, acc: torch.Tensor, bg_softmax: torch.Tensor, valid_mask: Optional[torch.Tensor] = None):
@@ -167,12 +195,12 @@ class SegmentationNetwork:
         assert bg_softmax.dtype == torch.float32 and bg_softmax.is_contiguous()
         if valid_mask is not None:
             assert valid_mask.dtype == torch.float32 and valid_mask.is_contiguous() and valid_mask.shape == acc.shape
-        check(self._lib.dwmh_ensemble_masked_add(self._ctx, _ptr(acc), _ptr(bg_softmax), _ptr(valid_mask), acc.numel(), _stream()))
+        check(self._lib.dwmh_ensemble_masked_add(self._ctx, _ptr(acc), _ptr(bg_softmax), _ptr(valid_mask), acc.numel(), self._st()))
 
     def ensemble_refine_(self, acc: torch.Tensor, k: int) -> torch.Tensor:
         """acc /= k in place (the ensembled field) -> uint8 label `field < 0.5` (DCNN_multistage.py:118-119)."""
         label = torch.empty(acc.shape, dtype=torch.uint8, device=acc.device)
-        check(self._lib.dwmh_ensemble_refine(self._ctx, _ptr(acc), int(k), _ptr(label), acc.numel(), _stream()))
+        check(self._lib.dwmh_ensemble_refine(self._ctx, _ptr(acc), int(k), _ptr(label), acc.numel(), self._st()))
         return label
 
     def remove_sparks(self, seg: torch.Tensor, min_volume: int = 3) -> torch.Tensor:
@@ -181,7 +209,7 @@ class SegmentationNetwork:
         assert seg.is_cuda and seg.dtype == torch.uint8 and seg.is_contiguous() and seg.dim() == 3
         out = torch.empty_like(seg)
         X, Y, Z = seg.shape
-        check(self._lib.dwmh_remove_sparks(self._ctx, _ptr(seg), X, Y, Z, int(min_volume), _ptr(out), _stream()))
+        check(self._lib.dwmh_remove_sparks(self._ctx, _ptr(seg), X, Y, Z, int(min_volume), _ptr(out), self._st()))
         return out
 
     def remove_3mm_sparks(self, seg: torch.Tensor, voxel_size: Sequence[float]) -> torch.Tensor:
@@ -201,18 +229,18 @@ class SegmentationNetwork:
         assert patches.is_cuda and patches.dtype == torch.float32 and patches.is_contiguous()
         n = patches.shape[0]
         out = torch.empty((n, 2) + tuple(self.patch_size), dtype=torch.float32, device=patches.device)
-        check(self._lib.dwmh_forward_patches(self._ctx, _ptr(patches), n, _ptr(out), _stream()))
+        check(self._lib.dwmh_forward_patches(self._ctx, _ptr(patches), n, _ptr(out), self._st()))
         return out
 
     def layer_output(self, index: int, n: int = 1) -> torch.Tensor:
         """Normalised+activated output of layer `index` for the first n samples of the last forward,
         as fp32 [n, c, d, h, w] (test hook)."""
         dims = (C.c_int32 * 5)()
-        check(self._lib.dwmh_debug_layer_output(self._ctx, index, C.c_void_p(0), 0, dims, _stream()))
+        check(self._lib.dwmh_debug_layer_output(self._ctx, index, C.c_void_p(0), 0, dims, self._st()))
         per = int(dims[1]) * int(dims[2]) * int(dims[3]) * int(dims[4])
         n = min(n, int(dims[0]))
         buf = torch.empty(n * per, dtype=torch.float32, device=self.device)
-        check(self._lib.dwmh_debug_layer_output(self._ctx, index, _ptr(buf), buf.numel(), dims, _stream()))
+        check(self._lib.dwmh_debug_layer_output(self._ctx, index, _ptr(buf), buf.numel(), dims, self._st()))
         return buf.view(n, int(dims[1]), int(dims[2]), int(dims[3]), int(dims[4]))
 
     def num_layers(self) -> int:
@@ -256,11 +284,21 @@ class SegmentationNetwork:
             raise NotImplementedError("only zero constant padding is supported")
         if x.shape[0] != self.input_channels:
             raise ValueError("expected %d input channel(s)" % self.input_channels)
-        if isinstance(x, torch.Tensor):
-            x = x.detach().float().cpu().numpy()
-        data, slicer = pad_nd_image(np.asarray(x, dtype=np.float32), self.patch_size, pad_border_mode, pad_kwargs)
         with torch.cuda.device(self.device):
-            vol = torch.from_numpy(np.ascontiguousarray(data[0])).to(self.device, non_blocking=False)
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                # device input stays on the device: zero padding (a10) with the same below / above split as pad_nd_image
+                vol = x.detach()[0].to(device=self.device, dtype=torch.float32)
+                diff = [max(p - s, 0) for p, s in zip(self.patch_size, vol.shape)]
+                pads = [(d // 2, d // 2 + d % 2) for d in diff]
+                if any(diff):
+                    vol = torch.nn.functional.pad(vol, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
+                vol = vol.contiguous()
+                slicer = (slice(None),) + tuple(slice(b, vol.shape[i] - a) for i, (b, a) in enumerate(pads))
+            else:
+                if isinstance(x, torch.Tensor):
+                    x = x.detach().float().numpy()
+                data, slicer = pad_nd_image(np.asarray(x, dtype=np.float32), self.patch_size, pad_border_mode, pad_kwargs)
+                vol = torch.from_numpy(np.ascontiguousarray(data[0])).to(self.device, non_blocking=False)
             X, Y, Z = vol.shape
             agg = torch.zeros((self.num_classes, X, Y, Z), dtype=torch.float32, device=self.device)
             wgt = torch.zeros((X, Y, Z), dtype=torch.float32, device=self.device)
@@ -276,11 +314,12 @@ class nnUNetTrainerV2:
     """The slice of the trainer surface `predict_cases` uses [U:nnUNetTrainerV2.py], B200-backed."""
 
     def __init__(self, plans: Dict, device: int = 0, act_dtype: str = "fp16", max_batch: int = 8,
-                 exact_scipy_gaussian: bool = True):
+                 exact_scipy_gaussian: bool = True, share_workspace_with: "Optional[nnUNetTrainerV2]" = None):
         self.plans = plans
         self.process_plans(plans)
         self.data_aug_params = {"do_mirror": True, "mirror_axes": (0, 1, 2)}
-        self.network = SegmentationNetwork(plans, device, act_dtype, max_batch)
+        self.network = SegmentationNetwork(plans, device, act_dtype, max_batch,
+                                           share_workspace_with.network if share_workspace_with is not None else None)
         if exact_scipy_gaussian:
             self.network.install_scipy_gaussian()
 
@@ -337,17 +376,27 @@ class nnUNetTrainerV2:
     # C-ABI host-buffer call (the end-to-end path bench.py times)
     def predict_raw_volume_host(self, vol: np.ndarray, zscore_mask_mode: int = 2, do_mirroring: bool = True,
                                 mirror_axes=(0, 1, 2), step_size: float = 0.5, use_gaussian: bool = True,
-                                out_softmax: Optional[np.ndarray] = None, out_seg: Optional[np.ndarray] = None):
+                                out_softmax: Optional[np.ndarray] = None, out_seg: Optional[np.ndarray] = None,
+                                seg_mask: Optional[np.ndarray] = None):
         """raw fp32 [X,Y,Z] host volume -> (seg uint8 [X,Y,Z], softmax fp32 [2,X,Y,Z]); z-score, H2D,
-        tiled prediction, finalize and D2H all inside dwmh_predict_volume_host."""
+        tiled prediction, finalize and D2H all inside dwmh_predict_volume_host.  seg_mask: nnU-Net's crop mask
+        (int8, >= 0 inside) -> normalisation over that mask (dwmh_predict_volume_host_masked)."""
         assert vol.dtype == np.float32 and vol.ndim == 3 and vol.flags.c_contiguous
         X, Y, Z = vol.shape
         sm = out_softmax if out_softmax is not None else np.empty((2, X, Y, Z), dtype=np.float32)
         sg = out_seg if out_seg is not None else np.empty((X, Y, Z), dtype=np.uint8)
         net = self.network
+        if seg_mask is not None:
+            assert seg_mask.dtype == np.int8 and seg_mask.shape == vol.shape and seg_mask.flags.c_contiguous
+            with torch.cuda.device(net.device):
+                check(net._lib.dwmh_predict_volume_host_masked(
+                    net._ctx, vol.ctypes.data_as(C.c_void_p), seg_mask.ctypes.data_as(C.c_void_p), X, Y, Z, float(step_size),
+                    int(bool(do_mirroring)), mirror_axes_mask(mirror_axes), int(bool(use_gaussian)),
+                    sm.ctypes.data_as(C.c_void_p), sg.ctypes.data_as(C.c_void_p), net._st()))
+            return sg, sm
         with torch.cuda.device(net.device):
             check(net._lib.dwmh_predict_volume_host(
                 net._ctx, vol.ctypes.data_as(C.c_void_p), X, Y, Z, int(zscore_mask_mode), float(step_size),
                 int(bool(do_mirroring)), mirror_axes_mask(mirror_axes), int(bool(use_gaussian)),
-                sm.ctypes.data_as(C.c_void_p), sg.ctypes.data_as(C.c_void_p), _stream()))
+                sm.ctypes.data_as(C.c_void_p), sg.ctypes.data_as(C.c_void_p), net._st()))
         return sg, sm

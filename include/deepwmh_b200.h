@@ -52,6 +52,11 @@ int dwmh_version(void);
 /* --- life cycle (replaces load_model_and_checkpoint_files + trainer.initialize(False)) ---------- */
 int dwmh_create(dwmh_ctx** out, int device, const dwmh_net_desc* desc);
 int dwmh_destroy(dwmh_ctx* ctx);
+/* A further model on the same device that BORROWS the activation workspaces of `parent` (k resident models of the
+ * checkpoint ensemble, predict_cases' `for p in params` loop / DCNN_multistage.py:320-345: ~60 MB of packed weights per
+ * model instead of another set of activation buffers).  Same dwmh_net_desc as the parent.  The parent's weights must be
+ * committed first, the parent must outlive the borrower, and contexts sharing workspaces run on ONE stream at a time. */
+int dwmh_create_like(dwmh_ctx** out, dwmh_ctx* parent);
 
 /* trainer.load_checkpoint_ram: one call per state_dict entry, nnU-Net key names
  * ("conv_blocks_context.0.blocks.0.conv.weight", "tu.3.weight", "seg_outputs.4.weight", ...),
@@ -91,6 +96,12 @@ int dwmh_predict_3d(dwmh_ctx* ctx, const float* vol_dev, int32_t X, int32_t Y, i
                     double step_size, int32_t do_mirroring, int32_t mirror_axes_mask, int32_t use_gaussian,
                     float* agg_dev, float* wgt_dev, int32_t tile_begin, int32_t tile_end, void* stream);
 
+/* The weight buffer the complete tile set leaves behind (wgt of dwmh_predict_3d over all tiles, bit-identical: the
+ * importance map of the covering tiles added per voxel in tile order).  It does not depend on the data, so a rank of a
+ * tile-sharded run computes it locally and only agg crosses NVLink.  Overwrites wgt_dev fp32 [X][Y][Z]. */
+int dwmh_weight_map(dwmh_ctx* ctx, int32_t X, int32_t Y, int32_t Z, double step_size, int32_t use_gaussian,
+                    float* wgt_dev, void* stream);
+
 /* class_probabilities = agg / wgt ; seg = argmax over classes (first maximum wins).
  * softmax_dev fp32 [2][X][Y][Z] (may alias agg_dev), seg_dev uint8 [X][Y][Z]; either may be NULL. */
 int dwmh_finalize(dwmh_ctx* ctx, const float* agg_dev, const float* wgt_dev, float* softmax_dev,
@@ -118,7 +129,7 @@ int dwmh_remove_sparks(dwmh_ctx* ctx, const uint8_t* seg_dev, int32_t X, int32_t
 /* --- stage-1 NLL anomaly map (deepwmh/analysis/lesion_analysis.py:84-176) ---------------------------
  * Context-free (no network involved): `device` is the CUDA ordinal; every buffer is a caller-owned device pointer,
  * volumes fp32 [X][Y][Z], masks fp32 with the reference's `> 0.5` convention.  fp64 arithmetic per voxel, fp32 storage.
- * Every call makes `device` the calling thread's current CUDA device (cudaSetDevice) and enqueues on `stream`.
+ * Every call runs on `device`, enqueues on `stream` and restores the calling thread's current CUDA device on return.
  *
  * dwmh_s1_zscore: z_score (deepwmh/analysis/image_ops.py:172-179, masked_mean/std :13-21) in place:
  *   x = (x - mean_mask) / max(std_mask, 1e-5) for ALL voxels (mask NULL = statistics over everything).
@@ -205,6 +216,13 @@ int dwmh_predict_volume_host(dwmh_ctx* ctx, const float* vol_host, int32_t X, in
                              int32_t zscore_mask_mode, double step_size, int32_t do_mirroring,
                              int32_t mirror_axes_mask, int32_t use_gaussian,
                              float* softmax_host, uint8_t* seg_host, void* stream);
+
+/* The same with nnU-Net's own normalisation mask (mask_mode 1): seg_mask_host int8 [X][Y][Z], >= 0 inside the
+ * hole-filled non-zero crop mask (crop_to_nonzero [U:preprocessing/cropping.py]), -1 outside. */
+int dwmh_predict_volume_host_masked(dwmh_ctx* ctx, const float* vol_host, const int8_t* seg_mask_host,
+                                    int32_t X, int32_t Y, int32_t Z, double step_size, int32_t do_mirroring,
+                                    int32_t mirror_axes_mask, int32_t use_gaussian,
+                                    float* softmax_host, uint8_t* seg_host, void* stream);
 
 /* --- test / profiling hooks ----------------------------------------------------------------------
  * Generic_UNet.forward + softmax on n patches: patches_dev fp32 [n][px][py][pz] -> probs_dev fp32 [n][2][px][py][pz]. */

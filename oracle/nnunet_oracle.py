@@ -276,7 +276,13 @@ def mirror_and_predict(net: Generic_UNet, x: torch.Tensor, mirror_axes=(0, 1, 2)
                        do_mirroring=True, mult: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[U::_internal_maybe_mirror_and_pred_3D]  x [1,C,px,py,pz] -> [1,classes,px,py,pz] fp32:
     sum_m (1/2^len(axes)) * unflip(softmax(net(flip_m x))), then *= gaussian."""
-    result = torch.zeros([1, net.num_classes] + list(x.shape[2:]), dtype=torch.float32)
+    # the reference moves the tile to the network's device and brings the result back (all_in_gpu=False); on a CPU
+    # network both moves are no-ops.  A CUDA network is only used by the GPU parity tests (fp32, TF32 off).
+    dev = next(net.parameters()).device if hasattr(net, "parameters") else x.device
+    x = x.to(dev)
+    if mult is not None:
+        mult = mult.to(dev)
+    result = torch.zeros([1, net.num_classes] + list(x.shape[2:]), dtype=torch.float32, device=dev)
     n_mirror = 8 if do_mirroring else 1
     num_results = 2 ** len(mirror_axes) if do_mirroring else 1
     for m in range(n_mirror):
@@ -290,7 +296,7 @@ def mirror_and_predict(net: Generic_UNet, x: torch.Tensor, mirror_axes=(0, 1, 2)
         result += 1 / num_results * pred
     if mult is not None:
         result[:, :] *= mult
-    return result
+    return result.cpu()
 
 
 @torch.no_grad()
