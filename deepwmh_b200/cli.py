@@ -72,41 +72,18 @@ def _check_cases(case_names: List[str], images: List[str]):
             sys.exit(1)
 
 
-def predict_case(trainer, plans: Dict, in_file: str, out_file: str, softmax_file: str = None, post3mm_file: str = None):
-    """One case through crop -> z-score -> tiled prediction -> paste back, the way nnUNet_predict does for a single
-    modality."""
-    import torch
-    vol_xyz, hdr = nifti.read_nifti(in_file)
-    data = np.ascontiguousarray(np.transpose(vol_xyz, (2, 1, 0)))[None]             # SimpleITK order (z, y, x)
-    stage = max(plans["plans_per_stage"].keys())
-    preprocess.check_spacing(hdr["spacing"][::-1], plans["plans_per_stage"][stage]["current_spacing"])
-    tf = list(plans.get("transpose_forward", [0, 1, 2]))
+def predict_case(trainer, plans: Dict, in_file: str, out_file: str, softmax_file: str = None, post3mm_file: str = None,
+                 do_mirroring: bool = True):
+    """One case the way nnUNet_predict's predict_cases does it for a single modality: preprocess_patient
+    (crop -> transpose -> resample -> z-score), tiled prediction, transpose back, resample back, argmax, paste back, NIfTI.
+    Everything between the file read and the file write stays on the device."""
+    data, _, props = trainer.preprocess_patient([in_file], as_numpy=False)
+    _, softmax = trainer.predict_preprocessed_data_return_seg_and_softmax(
+        data, do_mirroring=do_mirroring, mirror_axes=trainer.data_aug_params["mirror_axes"], use_sliding_window=True,
+        step_size=0.5, use_gaussian=True, all_in_gpu=False, mixed_precision=True, return_device_tensors=True)
     tb = list(plans.get("transpose_backward", [0, 1, 2]))
-    cropped, seg, bbox = preprocess.crop_to_nonzero(data)
-    cropped = np.ascontiguousarray(cropped.transpose([0] + [i + 1 for i in tf]))
-    seg = np.ascontiguousarray(seg.transpose([0] + [i + 1 for i in tf]))
-    cropped[np.isnan(cropped)] = 0
-    net = trainer.network
-    use_mask = bool(plans.get("use_mask_for_norm", {0: False})[0])
-    with torch.cuda.device(net.device):
-        v = torch.from_numpy(cropped[0]).to(net.device)
-        s = torch.from_numpy(seg[0]).to(net.device) if use_mask else None
-        net.normalize_(v, s, 1 if use_mask else 0)
-        norm = v.cpu().numpy()[None]
-    seg_pred, softmax = trainer.predict_preprocessed_data_return_seg_and_softmax(
-        norm, do_mirroring=True, mirror_axes=trainer.data_aug_params["mirror_axes"], use_sliding_window=True,
-        step_size=0.5, use_gaussian=True, all_in_gpu=False, mixed_precision=True)
-    seg_pred = seg_pred.transpose(tb)
-    full = preprocess.paste_back(seg_pred.astype(np.uint8), data.shape[1:], bbox)
-    nifti.write_nifti(out_file, np.transpose(full, (2, 1, 0)), hdr, dtype=np.uint8)
-    if post3mm_file is not None:                                                   # predict.py:158-163, on the device
-        with torch.cuda.device(net.device):
-            clean = net.remove_3mm_sparks(torch.from_numpy(full).to(net.device), list(hdr["spacing"])).cpu().numpy()
-        nifti.write_nifti(post3mm_file, np.transpose(clean, (2, 1, 0)).astype(np.float32), hdr, dtype=np.float32)
-    if softmax_file is not None:                                                   # the fork's --save_softmax: background channel
-        bg = np.ones(data.shape[1:], dtype=np.float32)
-        bg[tuple(slice(b[0], b[1]) for b in bbox)] = softmax[0].transpose(tb)
-        nifti.write_nifti(softmax_file, np.transpose(bg, (2, 1, 0)), hdr, dtype=np.float32)
+    softmax = softmax.permute([0] + [i + 1 for i in tb])
+    preprocess.save_segmentation_nifti_from_softmax(trainer.network, softmax, out_file, props, 1, None, softmax_file, post3mm_file)
 
 
 def _worker(gpu: int, cases: List[Tuple[str, str, str, str]], model: Dict[str, str]):

@@ -118,7 +118,10 @@ struct dwmh_ctx {
   int64_t launches = 0; double conv_flops = 0.0;
   bool stage_timing = false; float stage_ms[4] = {0, 0, 0, 0};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  std::vector<cudaEvent_t> tcev; int tcev_used = 0; double tc_ms = 0.0, tc_flops = 0.0, tc_launches = 0.0;   // per-launch timing of the tcgen05 kernel (stage timing only)
+  // per-launch timing by kernel class (stage timing only): 0 = conv3_tc_kernel, 1 = instnorm_lrelu_kernel, 2 = head_softmax_kernel
+  std::vector<cudaEvent_t> tcev; std::vector<int> tcev_cls; int tcev_used = 0;
+  double tc_ms = 0.0, tc_flops = 0.0, tc_launches = 0.0;
+  double cls_ms[3] = {0, 0, 0}, cls_bytes[3] = {0, 0, 0}, cls_launches[3] = {0, 0, 0};
   int num_sms = 148;
   int64_t P() const { return (int64_t)d.patch_size[0] * d.patch_size[1] * d.patch_size[2]; }
 };
@@ -259,6 +262,11 @@ extern "C" int dwmh_set_force_generic(dwmh_ctx* c, int32_t on) { if (!c) return 
 extern "C" int dwmh_get_counters(dwmh_ctx* c, int64_t* k, double* f) { if (!c) return fail("null ctx"); if (k) *k = c->launches; if (f) *f = c->conv_flops; return 0; }
 extern "C" int dwmh_set_stage_timing(dwmh_ctx* c, int32_t on) { if (!c) return fail("null ctx"); c->stage_timing = on != 0; return 0; }
 extern "C" int dwmh_get_stage_timing(dwmh_ctx* c, float out[4]) { if (!c) return fail("null ctx"); memcpy(out, c->stage_ms, sizeof c->stage_ms); return 0; }
+extern "C" int dwmh_get_kernel_timing(dwmh_ctx* c, double out[9]) {
+  if (!c) return fail("null ctx");
+  for (int i = 0; i < 3; ++i) { out[3 * i] = c->cls_ms[i]; out[3 * i + 1] = c->cls_bytes[i]; out[3 * i + 2] = c->cls_launches[i]; }
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // weights
@@ -571,11 +579,21 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
                         const SampleMeta* metas, int nb, cudaStream_t st) {
   if (nb > c->max_batch) return fail("forward: batch %d > max_batch %d", nb, c->max_batch);
   CU_TRY(cudaMemsetAsync(c->stats_arena, 0, c->stats_bytes, st));
-  auto tc_timed = [&](Layer& L, auto&& launch) -> int {
+  // stage timing: CUDA events around single launches, grouped by kernel class (the stats_reduce_kernel that follows a
+  // conv launch is inside the conv's pair: it is part of producing the layer)
+  auto cls_timed = [&](int cls, double bytes, auto&& launch) -> int {
     const bool timed = c->stage_timing && c->tcev_used + 2 <= (int)c->tcev.size();
     if (timed) CU_TRY(cudaEventRecord(c->tcev[c->tcev_used], st));
     DW_TRY(launch());
-    if (timed) { CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st)); c->tcev_used += 2; c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
+    if (timed) {
+      CU_TRY(cudaEventRecord(c->tcev[c->tcev_used + 1], st));
+      c->tcev_cls[c->tcev_used / 2] = cls; c->tcev_used += 2; c->cls_bytes[cls] += bytes; c->cls_launches[cls] += 1;
+    }
+    return 0;
+  };
+  auto tc_timed = [&](Layer& L, auto&& launch) -> int {
+    DW_TRY(cls_timed(0, 0.0, launch));
+    if (c->stage_timing) { c->tc_flops += L.flops_per_sample() * nb; c->tc_launches += 1; }
     c->launches += L.kind == L_TCONV ? 1 : 2;      // conv3_tc_kernel (+ stats_reduce_kernel)
     return 0;
   };
@@ -635,14 +653,16 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
       const int gx = (int)std::min<int64_t>((V / 2 + 255) / 256, 1024);      // a thread handles voxel pairs (256-bit accesses)
       dim3 grid(std::max(gx, 1), nb * (L.cout >> 3));
       S2dParams sp{L.s2d, L.out_sp[0], L.out_sp[1], L.out_sp[2], L.s2d_s[0], L.s2d_s[1], L.s2d_s[2]};
-      instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, norm_of(L), L.cout, V, sp);
+      const double bytes = (double)nb * L.cout * V * ((L.raw32 ? 4 : 2) + 2 + (L.s2d ? 2 : 0));
+      DW_TRY(cls_timed(1, bytes, [&] { instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, norm_of(L), L.cout, V, sp); return 0; }));
       c->launches++;
     }
   }
   // head: norm-on-load + 1x1x1 + softmax
   Layer& L = c->layers[c->last_conv];
   dim3 grid((unsigned)((L.vout() + 255) / 256), nb);
-  head_softmax_kernel<T><<<grid, 256, 4 * L.cout * sizeof(float), st>>>((const T*)L.out, norm_of(L), c->w_head_dev, c->probs, L.cout, L.vout());
+  DW_TRY(cls_timed(2, (double)nb * L.vout() * (2.0 * L.cout + 8.0), [&] {
+    head_softmax_kernel<T><<<grid, 256, 4 * L.cout * sizeof(float), st>>>((const T*)L.out, norm_of(L), c->w_head_dev, c->probs, L.cout, L.vout()); return 0; }));
   c->launches++;
   c->conv_flops += 2.0 * L.vout() * L.cout * c->d.num_classes * nb;
   CU_TRY(cudaGetLastError());
@@ -741,8 +761,10 @@ extern "C" int dwmh_predict_3d(dwmh_ctx* c, const float* vol, int32_t X, int32_t
   const int64_t P = c->P();
   float conv_ms = 0.f, agg_ms = 0.f;
   if (c->stage_timing) {
-    while (c->tcev.size() < 128) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); c->tcev.push_back(e); }
+    while (c->tcev.size() < 256) { cudaEvent_t e; CU_TRY(cudaEventCreate(&e)); c->tcev.push_back(e); }
+    c->tcev_cls.assign(c->tcev.size() / 2, 0);
     c->tcev_used = 0; c->tc_ms = 0; c->tc_flops = 0; c->tc_launches = 0;
+    for (int i = 0; i < 3; ++i) { c->cls_ms[i] = 0; c->cls_bytes[i] = 0; c->cls_launches[i] = 0; }
   }
   // Batches of forwards and the overlap-add of their tiles alternate on the caller's stream, tiles in order (deterministic).
   for (int t0 = 0; t0 < nt; t0 += tiles_per_batch) {
@@ -762,7 +784,11 @@ extern "C" int dwmh_predict_3d(dwmh_ctx* c, const float* vol, int32_t X, int32_t
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); cudaEventElapsedTime(&b, c->ev[1], c->ev[2]);
       conv_ms += a; agg_ms += b;
-      for (int i = 0; i + 1 < c->tcev_used; i += 2) { float t = 0; cudaEventElapsedTime(&t, c->tcev[i], c->tcev[i + 1]); c->tc_ms += t; }
+      for (int i = 0; i + 1 < c->tcev_used; i += 2) {
+        float t = 0; cudaEventElapsedTime(&t, c->tcev[i], c->tcev[i + 1]);
+        c->cls_ms[c->tcev_cls[i / 2]] += t;
+        if (c->tcev_cls[i / 2] == 0) c->tc_ms += t;
+      }
       c->tcev_used = 0;
     }
   }

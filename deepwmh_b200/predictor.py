@@ -262,9 +262,11 @@ class SegmentationNetwork:
                    use_sliding_window: bool = False, step_size: float = 0.5,
                    patch_size: Tuple[int, ...] = None, regions_class_order: Tuple[int, ...] = None,
                    use_gaussian: bool = False, pad_border_mode: str = "constant", pad_kwargs: dict = None,
-                   all_in_gpu: bool = False, verbose: bool = True, mixed_precision: bool = True):
+                   all_in_gpu: bool = False, verbose: bool = True, mixed_precision: bool = True,
+                   return_device_tensors: bool = False):
         """[U:SegmentationNetwork.predict_3D].  x: (c, x, y, z) numpy fp32 or CUDA tensor.
-        Returns (seg int64 [x,y,z], class_probabilities fp32 [classes,x,y,z]) as numpy arrays."""
+        Returns (seg int64 [x,y,z], class_probabilities fp32 [classes,x,y,z]) as numpy arrays, or -- additive flag
+        return_device_tensors -- (seg uint8, probabilities fp32) as CUDA tensors without the device-to-host copies."""
         assert step_size <= 1, "step_size must be smaller than 1. Otherwise there will be a gap between consecutive predictions"
         assert len(x.shape) == 4, "data must have shape (c,x,y,z)"
         if not self._weights_loaded:
@@ -305,6 +307,8 @@ class SegmentationNetwork:
             self.accumulate_tiles(vol, agg, wgt, step_size, do_mirroring, mirror_axes, use_gaussian)
             seg, probs = self.finalize(agg, wgt)
             sl = tuple(slicer[1:])
+            if return_device_tensors:
+                return seg[sl], probs[(slice(None),) + sl]
             seg_np = seg[sl].cpu().numpy().astype(np.int64)
             probs_np = probs[(slice(None),) + sl].cpu().numpy()
         return seg_np, probs_np
@@ -345,15 +349,21 @@ class nnUNetTrainerV2:
         sd = {(k[7:] if k.startswith("module.") else k): v for k, v in checkpoint["state_dict"].items()}
         self.network.load_state_dict(sd)
 
-    def preprocess_patient(self, input_files):
-        raise NotImplementedError("file-level preprocessing (crop/resample) is outside this path; "
-                                  "see SURVEY.md section 8f-1")
+    def preprocess_patient(self, input_files, as_numpy: bool = True):
+        """[U:nnUNetTrainer.preprocess_patient] -> (data [c, x, y, z] fp32, seg [1, x, y, z], properties): crop_to_nonzero,
+        transpose_forward, resample to the plans' spacing and z-score (the last two on the device).  as_numpy=False keeps
+        data / seg on the device (the predictor accepts CUDA tensors)."""
+        from . import preprocess
+        d, s, props = preprocess.preprocess_test_case(self.network, self.plans, list(input_files))
+        if as_numpy:
+            return d.cpu().numpy(), s.cpu().numpy(), props
+        return d, s, props
 
     def predict_preprocessed_data_return_seg_and_softmax(
             self, data, do_mirroring: bool = True, mirror_axes: Tuple[int] = None,
             use_sliding_window: bool = True, step_size: float = 0.5, use_gaussian: bool = True,
             pad_border_mode: str = "constant", pad_kwargs: dict = None, all_in_gpu: bool = False,
-            verbose: bool = True, mixed_precision=True) -> Tuple[np.ndarray, np.ndarray]:
+            verbose: bool = True, mixed_precision=True, return_device_tensors: bool = False) -> Tuple[np.ndarray, np.ndarray]:
         if pad_border_mode == "constant" and pad_kwargs is None:
             pad_kwargs = {"constant_values": 0}
         if do_mirroring and mirror_axes is None:
@@ -369,7 +379,7 @@ class nnUNetTrainerV2:
                                       patch_size=self.patch_size, regions_class_order=None,
                                       use_gaussian=use_gaussian, pad_border_mode=pad_border_mode,
                                       pad_kwargs=pad_kwargs, all_in_gpu=all_in_gpu, verbose=verbose,
-                                      mixed_precision=mixed_precision)
+                                      mixed_precision=mixed_precision, return_device_tensors=return_device_tensors)
         self.network.do_ds = ds
         return ret
 

@@ -209,6 +209,19 @@ int dwmh_s1_label_vote(int32_t device, const float* const* labels, int32_t k, in
 int dwmh_s1_apply_priors(int32_t device, float* anomaly_dev, const float* anomaly_median_dev, const float* averaged_label_dev,
                          const float* tissue_majority_dev, int32_t stage, int64_t n, void* stream);
 
+/* --- spacing resample (resample_data_or_seg [U:preprocessing/preprocessing.py]; the resample-back of
+ * save_segmentation_nifti_from_softmax [U:inference/segmentation_export.py]) on the device, context-free.
+ * skimage.transform.resize(order, mode='edge', anti_aliasing=False, clip=True) semantics, fp64 arithmetic:
+ *   src_dev fp32 [in_shape] -> dst_dev [out_shape]; order 3 (image data), 1 (crop mask, softmax) or 0;
+ *   separate_axis >= 0: nnU-Net's "separate z" rule -- the resize runs per slice orthogonal to that axis and the axis
+ *   itself is resampled nearest-neighbour (order_z = 0); -1: full 3-D resize.
+ *   out_mode 0: dst fp32.  out_mode 1: dst int8 = (value >= 0.5 ? 0 : -1), i.e. resize_segmentation of nnU-Net's
+ *   {-1, 0} crop mask when src is the 0/1 indicator of label 0.
+ * workspace_dev: dwmh_resample_workspace() bytes of device memory. */
+int dwmh_resample_workspace(const int32_t in_shape[3], int32_t order, int32_t separate_axis, int64_t* bytes);
+int dwmh_resample(int32_t device, const float* src_dev, const int32_t in_shape[3], void* dst_dev, const int32_t out_shape[3],
+                  int32_t order, int32_t separate_axis, int32_t out_mode, void* workspace_dev, void* stream);
+
 /* --- a6 end to end with HOST buffers (what predict_preprocessed_data_return_seg_and_softmax does):
  * raw fp32 volume [X][Y][Z] in host memory -> (optional z-score, mask_mode as above, <0 = skip)
  * -> tiled prediction -> host softmax fp32 [2][X][Y][Z] and seg uint8 [X][Y][Z].  H2D/D2H inside. */
@@ -242,6 +255,9 @@ int dwmh_get_counters(dwmh_ctx* ctx, int64_t* kernel_launches, double* conv_flop
  * (CUDA events around every launch), out[3]=TFLOP those launches computed.  Only filled when enabled (adds syncs). */
 int dwmh_set_stage_timing(dwmh_ctx* ctx, int32_t on);
 int dwmh_get_stage_timing(dwmh_ctx* ctx, float out_ms[4]);
+/* Per kernel class of the last timed dwmh_predict_3d: out[3k + {0,1,2}] = {device ms, algorithmic bytes, launches} for
+ * k = 0 conv3_tc_kernel (bytes not counted here), 1 instnorm_lrelu_kernel, 2 head_softmax_kernel. */
+int dwmh_get_kernel_timing(dwmh_ctx* ctx, double out[9]);
 
 #ifdef __cplusplus
 }

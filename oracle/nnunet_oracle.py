@@ -300,11 +300,12 @@ def mirror_and_predict(net: Generic_UNet, x: torch.Tensor, mirror_axes=(0, 1, 2)
 
 
 @torch.no_grad()
-def predict_3D_tiled(net: Generic_UNet, x: np.ndarray, step_size: float, do_mirroring: bool,
-                     mirror_axes, patch_size, use_gaussian: bool, pad_border_mode="constant",
-                     pad_kwargs=None, return_buffers=False):
-    """[U::_internal_predict_3D_3Dconv_tiled] default branch (all_in_gpu=False: host fp32 numpy
-    aggregation).  x [C,X,Y,Z] -> (seg int64 [X,Y,Z], softmax fp32 [classes,X,Y,Z])."""
+def iter_predict_3D_tiled(net: Generic_UNet, x: np.ndarray, step_size: float, do_mirroring: bool,
+                          mirror_axes, patch_size, use_gaussian: bool, pad_border_mode="constant",
+                          pad_kwargs=None, return_buffers=False):
+    """[U::_internal_predict_3D_3Dconv_tiled] default branch (all_in_gpu=False: host fp32 numpy aggregation) as a
+    generator: yields ("tile", index, n_tiles) after every tile and finally ("done", result).  The generator form lets
+    bench.py's CPU arm time a bounded number of tiles of the very same code path."""
     assert x.ndim == 4, "x must be (c, x, y, z)"
     data, slicer = pad_nd_image(x, patch_size, pad_border_mode, pad_kwargs)
     shape = data.shape
@@ -321,6 +322,7 @@ def predict_3D_tiled(net: Generic_UNet, x: np.ndarray, step_size: float, do_mirr
         mult = None
     agg = np.zeros([net.num_classes] + list(shape[1:]), dtype=np.float32)
     nb = np.zeros([net.num_classes] + list(shape[1:]), dtype=np.float32)
+    done = 0
     for lx in steps[0]:
         for ly in steps[1]:
             for lz in steps[2]:
@@ -329,12 +331,27 @@ def predict_3D_tiled(net: Generic_UNet, x: np.ndarray, step_size: float, do_mirr
                 pred = mirror_and_predict(net, tile, mirror_axes, do_mirroring, mult)[0].numpy()
                 agg[(slice(None),) + sl] += pred
                 nb[(slice(None),) + sl] += add_nb
+                done += 1
+                yield ("tile", done, num_tiles)
     sl_out = (slice(0, agg.shape[0]),) + tuple(slicer[1:])
     agg, nb = agg[sl_out], nb[sl_out]
     if return_buffers:
-        return agg.copy(), nb.copy()
+        yield ("done", (agg.copy(), nb.copy()))
+        return
     probs = agg / nb
-    return probs.argmax(0), probs
+    yield ("done", (probs.argmax(0), probs))
+
+
+def predict_3D_tiled(net: Generic_UNet, x: np.ndarray, step_size: float, do_mirroring: bool,
+                     mirror_axes, patch_size, use_gaussian: bool, pad_border_mode="constant",
+                     pad_kwargs=None, return_buffers=False):
+    """[U::_internal_predict_3D_3Dconv_tiled]  x [C,X,Y,Z] -> (seg int64 [X,Y,Z], softmax fp32 [classes,X,Y,Z])."""
+    out = None
+    for kind, *payload in iter_predict_3D_tiled(net, x, step_size, do_mirroring, mirror_axes, patch_size, use_gaussian,
+                                                pad_border_mode, pad_kwargs, return_buffers):
+        if kind == "done":
+            out = payload[0]
+    return out
 
 
 def predict_3D(net: Generic_UNet, x: np.ndarray, do_mirroring: bool, mirror_axes=(0, 1, 2),
