@@ -370,7 +370,8 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
   // which producers need a parity-split copy (strided tcgen05 consumer)
   for (auto& L : c->layers) {
     const bool strided = L.s[0] != 1 || L.s[1] != 1 || L.s[2] != 1;
-    if (L.kind == L_CONV && strided && L.k[0] == 3 && L.k[1] == 3 && L.k[2] == 3 && L.c0 % 16 == 0 && L.c1 == 0 && L.cout % 16 == 0)
+    const bool k_ok = (L.k[0] == 3 || (L.k[0] == 1 && L.s[0] == 1)) && L.k[1] == 3 && L.k[2] == 3;      // what tc_prepare accepts
+    if (L.kind == L_CONV && strided && k_ok && L.c0 % 16 == 0 && L.c1 == 0 && L.cout % 16 == 0)
       for (int a_ = 0; a_ < 3; ++a_) c->layers[L.in0].s2d_s[a_] = L.s[a_];
   }
   // ---- activation buffers, statistics, probabilities (allocated once per context) ----

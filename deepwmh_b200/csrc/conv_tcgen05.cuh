@@ -600,6 +600,47 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         __syncwarp();
         continue;
       }
+      if (p.nclass == 1 && p.Jlo == 0 && p.Jhi == 0 && p.tiles_per_kc == 9 && fresh_from == zo_hi) {
+        // ---- 1x3x3 kernel, stride 1 (anisotropic plans): input plane t feeds output plane t alone -- 9 in-plane taps x
+        // KSTEPS MMAs of N = CB per channel chunk into the plane's own slot; the first MMA overwrites it.
+        const uint32_t col = tmem + lo_slot * CB;
+        for (int kc = 0; kc < p.nkc; ++kc) {
+          if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
+          tc::tc_fence_after();
+          { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
+          const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+          uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
+#pragma unroll
+          for (int sft = 0; sft < 9; ++sft) {
+            uint32_t b_lo0 = bl;
+            if (!p.resident) {
+              if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
+              tc::tc_fence_after();
+              b_lo0 = ((smem_b_d + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+              { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
+            }
+            if (leader) {
+#pragma unroll
+              for (int kk = 0; kk < KSTEPS; ++kk) {
+                const uint64_t adesc = tc_desc(a_hi, a_lo0 + (sft / 3) * TC_PW + (sft % 3) + kk * (2 * TC_PLANE_BYTES >> 4));
+                tc::umma_f16(col, adesc, tc_desc(b_hi, b_lo0 + kk * kstep_b), idesc1, (sft == 0 && kk == 0 && kc == 0) ? 0u : 1u);
+              }
+            }
+            if (!p.resident) {
+              if (elected) tc::umma_commit(b_empty + 8 * b.idx);
+              b.advance(NB);
+            }
+            bl += tile16;
+          }
+          if (elected) tc::umma_commit(a_empty + 8 * a.idx);
+          a.advance(SA);
+        }
+        if (elected) tc::umma_commit(acc_full + 8 * done.idx);        // output plane t is complete
+        done.advance(R);
+        ++next_done;
+        __syncwarp();
+        continue;
+      }
       if (p.s222 && zo_lo == t && zo_hi == t + 1 && fresh_from == zo_hi && 2 * CB <= 256) {
         // ---- steady state of a stride-(2,2,2) conv, straight line: the 8 parity classes and their 1/2/2/4 in-plane taps
         // are compile-time here (the tap loop below costs ~250 cycles per tap in loop / branch overhead alone, more than
@@ -1087,7 +1128,10 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
                       void* out, bool out32, std::string* why) {
   t.enabled = false;
   why->clear();
-  if (k[0] != 3 || k[1] != 3 || k[2] != 3) return 0;
+  // 3x3x3, or 1x3x3 (anisotropic plans: no taps and no stride along the thick-slice axis)
+  if ((k[0] != 3 && k[0] != 1) || k[1] != 3 || k[2] != 3) return 0;
+  const int kd = k[0];
+  if (kd == 1 && s[0] != 1) return 0;
   const bool strided = s[0] != 1 || s[1] != 1 || s[2] != 1;
   if (strided && c1 > 0) return 0;
   if (c0 % 16 || c1 % 16 || cout % 16) return 0;
@@ -1097,7 +1141,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   const int sd = s[0], sh = s[1], sw = s[2];
   kp.out32 = out32 ? 1 : 0;
   kp.tconv = 0; kp.CBt = 0; kp.osd = kp.osh = kp.osw = 1; kp.Cout_t = cout;
-  kp.nclass = sd * sh * sw; kp.Jlo = sd == 1 ? -1 : 0; kp.Jhi = 1; kp.jmax = sd == 1 ? 3 : 2;
+  kp.nclass = sd * sh * sw; kp.Jlo = (sd == 1 && kd == 3) ? -1 : 0; kp.Jhi = kd == 3 ? 1 : 0; kp.jmax = kd == 1 ? 1 : (sd == 1 ? 3 : 2);
   kp.Din = in_sp[0] / sd;
   struct Tap { int kh, kw; };
   std::vector<std::vector<Tap>> cls_taps(kp.nclass);
@@ -1110,7 +1154,8 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
         const int pd = sd == 2 ? 1 - cd : 0;
         TcClassDesc& cd_ = kp.cls[c];
         cd_.tapmask = 0; cd_.tile0 = tile0;
-        if (sd == 1) { cd_.jlo = -1; cd_.jcnt = 3; cls_kd[c] = {2, 1, 0}; }
+        if (kd == 1) { cd_.jlo = 0; cd_.jcnt = 1; cls_kd[c] = {0}; }
+        else if (sd == 1) { cd_.jlo = -1; cd_.jcnt = 3; cls_kd[c] = {2, 1, 0}; }
         else if (pd == 0) { cd_.jlo = 0; cd_.jcnt = 1; cls_kd[c] = {1}; }
         else { cd_.jlo = 0; cd_.jcnt = 2; cls_kd[c] = {2, 0}; }
         for (int dy = 0; dy < 3; ++dy)
@@ -1198,7 +1243,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
   kp.ncb = cout / CB; kp.SA = SA; kp.NB = NB; kp.resident = resident; kp.G = G;
   kp.xf_src = nullptr;
   kp.xform = 0; kp.xf_sums = nullptr; kp.xf_gamma = nullptr; kp.xf_beta = nullptr; kp.xf_inv_count = 0.0;
-  t.xform_ok = !strided && resident && c1 == 0 && KC == 32 && (cin == 32 || cin == 64) && CB <= 32 && SA >= 3;
+  t.xform_ok = !strided && kd == 3 && resident && c1 == 0 && KC == 32 && (cin == 32 || cin == 64) && CB <= 32 && SA >= 3;
   kp.R = std::min(TC_MAX_R, (512 / G) / CB);
   kp.fmt = bf16 ? 1 : 0;
   kp.a_stage_bytes = KC * 360; kp.b_tile_bytes = kp.jmax * CB * KC * 2;
@@ -1223,7 +1268,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
               for (int co_ = 0; co_ < CB; ++co_)
                 for (int e = 0; e < 8; ++e) {
                   const int co = cb * CB + co_, ci = kc * KC + k8 * 8 + e;
-                  const float v = w[((size_t)co * cin + ci) * 27 + cls_kd[c][r] * 9 + cls_taps[c][ti].kh * 3 + cls_taps[c][ti].kw];
+                  const float v = w[((size_t)co * cin + ci) * (kd * 9) + cls_kd[c][r] * 9 + cls_taps[c][ti].kh * 3 + cls_taps[c][ti].kw];
                   tile[((size_t)k8 * kp.jmax * CB + (size_t)r * CB + co_) * 8 + e] = tc_to_bits(v, bf16);
                 }
         }

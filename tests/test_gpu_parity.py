@@ -111,6 +111,36 @@ def test_anisotropic_plan_matches_oracle():
         ref = torch.softmax(net(x), 1).numpy()
     got = tr.network.forward_patches(x.cuda()).cpu().numpy()
     assert np.abs(got - ref).max() < 1e-2
+    # the 1x3x3 / stride (1,2,2) layers run on the tensor cores too; only the 1-channel first conv (9 taps) stays direct
+    kinds = [tr.network.layer_kernel_kind(i) for i in range(tr.network.num_layers())]
+    assert kinds[0] == 0 and all(k == 1 for k in kinds[1:]), kinds
+    tr.network.set_force_generic(True)                       # CUDA-core cross-check of the same plan
+    got_g = tr.network.forward_patches(x.cuda()).cpu().numpy()
+    tr.network.set_force_generic(False)
+    assert np.abs(got_g - ref).max() < 1e-2 and np.abs(got_g - got).max() < 1e-2
+    tr.network.close()
+
+
+def test_anisotropic_plan_every_layer_matches_oracle():
+    """Layer-level parity of a thick-slice plan: two 1x3x3 stages with (1,2,2) pooling, then 3x3x3."""
+    plans = small_plans(patch=(8, 64, 64), pools=((1, 2, 2), (1, 2, 2), (2, 2, 2)),
+                        kernels=[[1, 3, 3], [1, 3, 3], [3, 3, 3], [3, 3, 3]])
+    tr, net = _trainer(plans)
+    x = torch.randn(2, 1, 8, 64, 64, generator=torch.Generator().manual_seed(5))
+    acts, hooks = [], []
+    for m in net.modules():
+        if isinstance(m, (O.ConvDropoutNormNonlin, torch.nn.ConvTranspose3d)):
+            hooks.append(m.register_forward_hook(lambda mod, i, o: acts.append(o.detach().clone())))
+    with torch.no_grad():
+        net(x)
+    for h in hooks:
+        h.remove()
+    tr.network.forward_patches(x.cuda())
+    for li, ref in enumerate(acts):
+        got = tr.network.layer_output(li, n=2).cpu()
+        assert got.shape == ref.shape, (li, got.shape, ref.shape)
+        err = (got - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+        assert err < 2e-2, (li, err)
     tr.network.close()
 
 
