@@ -1069,6 +1069,13 @@ inline void tc_free(TcLayer& t) {
   t.enabled = false;
 }
 
+// activation-ring depth of the resident-weight plans (DWMH_TC_MAX_SA, default 4; <= 8: the barrier block has room for it)
+inline int tc_max_sa() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DWMH_TC_MAX_SA"); v = e ? std::max(2, std::min(8, atoi(e))) : TC_MAX_SA; }
+  return v;
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1196,7 +1203,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
       const long long btot = (long long)ntile * kp.jmax * cbt * kc * 2;
       if (btot + 2LL * 3 * a_stage <= budget) {
         KC = kc; CB = cbt; resident = 1; NB = ntile; G = 2;
-        SA = (int)std::min<long long>(TC_MAX_SA, (budget - btot) / (2LL * a_stage));
+        SA = (int)std::min<long long>(tc_max_sa(), (budget - btot) / (2LL * a_stage));
         break;
       }
     }
@@ -1222,7 +1229,7 @@ inline int tc_prepare(TcLayer& t, const std::vector<float>& w, int c0, int c1, i
         const long long btot = (long long)ntile * kp.jmax * cbt * kc * 2;
         if (btot + 2LL * a_stage <= budget) {
           KC = kc; CB = cbt; resident = 1; NB = ntile;
-          SA = (int)std::min<long long>(TC_MAX_SA, (budget - btot) / a_stage);
+          SA = (int)std::min<long long>(tc_max_sa(), (budget - btot) / a_stage);
           break;
         }
       }

@@ -82,3 +82,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_net_desc_layout_matches_the_header_and_the_integration_stub(tmp_path):
+    """dwmh_create copies the caller's dwmh_net_desc by value: the ctypes mirror, the header and the stub INTEGRATION.md
+    shows must agree field for field (round 1's stub was one int32 short)."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "deepwmh_b200.h"\n'
+                   'int main(void) { printf("%zu %zu %zu\\n", sizeof(dwmh_net_desc), offsetof(dwmh_net_desc, struct_size), offsetof(dwmh_net_desc, conv_kernel_sizes)); return 0; }\n')
+    exe = str(tmp_path / "sz")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)])
+    size, off_ss, off_ck = (int(v) for v in subprocess.check_output([exe]).split())
+    assert C.sizeof(_lib.NetDesc) == size and _lib.NetDesc.struct_size.offset == off_ss and _lib.NetDesc.conv_kernel_sizes.offset == off_ck
+    # the stub of INTEGRATION.md, executed
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class NetDesc\(ctypes\.Structure\):.*?\n(?=\nmodel_dir)", doc, flags=re.S)
+    assert m, "INTEGRATION.md no longer shows the NetDesc stub"
+    ns = {}
+    exec("import ctypes\n" + re.sub(r"#.*", "", m.group(0)), ns)
+    assert C.sizeof(ns["NetDesc"]) == size and ns["NetDesc"].struct_size.offset == off_ss
+    assert [f[0] for f in ns["NetDesc"]._fields_] == [f[0] for f in _lib.NetDesc._fields_]
