@@ -109,7 +109,8 @@ struct dwmh_ctx {
   dwmh_ctx* lender = nullptr;        // dwmh_create_like: activation workspaces are borrowed from this context
   float* gauss_dev = nullptr; std::vector<float> gauss_host; bool gauss_custom = false;
   SampleMeta* metas_dev = nullptr; size_t metas_cap = 0;
-  double* zs_acc = nullptr;
+  double* zs_acc = nullptr;          // z-score: [0..2] totals for the host, [4 ...] one {sum, sum of squares, count} slot per CTA
+  unsigned long long* zs_barrier = nullptr; unsigned long long zs_target = 0; int zs_grid = 0;
   int* ccl_labels = nullptr; int* ccl_sizes = nullptr; size_t ccl_cap_l = 0, ccl_cap_s = 0;   // dwmh_remove_sparks workspace
   // host-buffer path (grow only)
   float* hv_vol = nullptr; float* hv_pad = nullptr; float* hv_agg = nullptr; float* hv_wgt = nullptr; uint8_t* hv_seg = nullptr;
@@ -244,7 +245,7 @@ extern "C" int dwmh_destroy(dwmh_ctx* c) {
     free_dev(L.w_dev); free_dev(L.gamma_dev); free_dev(L.beta_dev); tc_free(L.tc);
   }
   if (!c->lender) { free_dev(c->stats_arena); free_dev(c->probs); free_dev(c->stat_partials); }
-  free_dev(c->w_head_dev); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc);
+  free_dev(c->w_head_dev); free_dev(c->gauss_dev); free_dev(c->metas_dev); free_dev(c->zs_acc); free_dev(c->zs_barrier);
   free_dev(c->hv_vol); free_dev(c->hv_pad); free_dev(c->hv_agg); free_dev(c->hv_wgt); free_dev(c->hv_seg);
   free_dev(c->ccl_labels); free_dev(c->ccl_sizes);
   for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -459,7 +460,6 @@ extern "C" int dwmh_commit_weights(dwmh_ctx* c) {
       if (P.has_norm && !P.raw32 && uses[L.in0] == 1 && P.s2d_s[0] * P.s2d_s[1] * P.s2d_s[2] == 1 && P.cout <= 64) P.fused_norm = true;
     }
   }
-  if (!c->zs_acc) CU_TRY(cudaMalloc((void**)&c->zs_acc, 4 * sizeof(double)));
   if (!c->gauss_custom) {
     c->gauss_host.resize(c->P());
     DW_TRY(dwmh_gaussian_map(c->d.patch_size, 1.0 / 8, c->gauss_host.data()));
@@ -552,12 +552,25 @@ extern "C" int dwmh_zscore(dwmh_ctx* c, float* vol, const int8_t* seg, int64_t n
   if ((reinterpret_cast<uintptr_t>(vol) & 15) || (seg && (reinterpret_cast<uintptr_t>(seg) & 3))) return fail("dwmh_zscore: buffers must be 16-byte (vol) / 4-byte (seg) aligned");
   cudaStream_t st = (cudaStream_t)stream_;
   DEV_GUARD(c->device);
-  if (!c->zs_acc) CU_TRY(cudaMalloc((void**)&c->zs_acc, 4 * sizeof(double)));
-  CU_TRY(cudaMemsetAsync(c->zs_acc, 0, 4 * sizeof(double), st));
-  const int grid = c->num_sms * 8;
-  zscore_reduce_kernel<<<grid, 256, 0, st>>>(vol, seg, n, mask_mode, c->zs_acc);
-  zscore_apply_kernel<<<grid, 256, 0, st>>>(vol, seg, n, mask_mode, c->zs_acc);
-  c->launches += 2;
+  if (!c->zs_acc) {
+    // one cooperative launch: every CTA must be resident at once
+    int per_sm = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, zscore_fused_kernel, 256, 0));
+    if (per_sm < 1) return fail("dwmh_zscore: the fused kernel does not fit an SM");
+    c->zs_grid = c->num_sms * std::min(per_sm, 4);
+    CU_TRY(cudaMalloc((void**)&c->zs_acc, (4 + 3 * (size_t)c->zs_grid) * sizeof(double)));
+    CU_TRY(cudaMalloc((void**)&c->zs_barrier, sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(c->zs_barrier, 0, sizeof(unsigned long long)));
+    c->zs_target = 0;
+  }
+  {
+    double* slots = c->zs_acc + 4; double* totals = c->zs_acc;
+    unsigned long long target = c->zs_target + (unsigned long long)c->zs_grid;
+    void* args[] = {(void*)&vol, (void*)&seg, (void*)&n, (void*)&mask_mode, (void*)&slots, (void*)&c->zs_barrier, (void*)&target, (void*)&totals};
+    CU_TRY(cudaLaunchCooperativeKernel((const void*)zscore_fused_kernel, dim3(c->zs_grid), dim3(256), args, 0, st));
+    c->zs_target = target;
+  }
+  c->launches += 1;
   CU_TRY(cudaGetLastError());
   if (stats_out) {
     double h[3];
@@ -827,7 +840,10 @@ extern "C" int dwmh_finalize(dwmh_ctx* c, const float* agg, const float* wgt, fl
   cudaStream_t st = (cudaStream_t)stream_;
   DEV_GUARD(c->device);
   const int64_t V = (int64_t)X * Y * Z;
-  finalize_kernel<<<c->num_sms * 8, 256, 0, st>>>(agg, wgt, softmax, seg, V);
+  const bool vec = (V & 3) == 0 && !((reinterpret_cast<uintptr_t>(agg) | reinterpret_cast<uintptr_t>(wgt) | reinterpret_cast<uintptr_t>(softmax)) & 15) &&
+                   !(reinterpret_cast<uintptr_t>(seg) & 3);
+  if (vec) finalize_kernel<true><<<c->num_sms * 8, 256, 0, st>>>(agg, wgt, softmax, seg, V);
+  else finalize_kernel<false><<<c->num_sms * 8, 256, 0, st>>>(agg, wgt, softmax, seg, V);
   c->launches++;
   CU_TRY(cudaGetLastError());
   return 0;

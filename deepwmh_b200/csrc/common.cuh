@@ -113,7 +113,7 @@ __device__ __forceinline__ void norm_coeffs(const NormParams& np, int n, int C, 
   b = (float)((double)np.beta[c] - mean * (double)np.gamma[c] * inv);
 }
 
-// One (count, mean, M2 = sum (x - mean)^2) partial of the tcgen05 conv epilogue: one per (work item, epilogue warp, channel).
+// One (count, mean, M2 = sum (x - mean)^2) partial of the tcgen05 conv epilogue: one per (work item, channel).
 struct StatPartial { float n, mean, m2, pad; };
 
 // Chan's pairwise update of (n, mean, M2) with a second partial; exact in real arithmetic, well conditioned in floating point.

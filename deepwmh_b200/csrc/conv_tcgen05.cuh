@@ -54,7 +54,7 @@ constexpr int TC_FIRST_STAGE_BYTES = 8 * 128 * 16;     // im2col operand of one 
 struct TcClassDesc { int tapmask, jlo, jcnt, tile0; };
 
 struct TcKParams {
-  const void* wpack; void* out; StatPartial* partials;   // partials: [item][4 epilogue warps][CB] (count, mean, M2)
+  const void* wpack; void* out; StatPartial* partials;   // partials: [item][CB] (count, mean, M2)
   int C0, C1, Cout, CB, KC, nkc, nkc0;
   int nclass, Jlo, Jhi, jmax, tiles_per_kc, Din;
   int out32;                                 // raw output stored as fp32 instead of T
@@ -76,16 +76,16 @@ struct TcKParams {
 };
 
 // Ordered second stage: every (sample, channel) combines the partials of its work items in index order, in fp64.
-// partials: [item][4 warps][CB]; the items of (n, cb) are the contiguous range [(n*ncb + cb) * ipb, +ipb).
+// partials: [item][CB]; the items of (n, cb) are the contiguous range [(n*ncb + cb) * ipb, +ipb).
 // grid = nb * ncb blocks of CB * jn threads (c fastest -> coalesced 16-byte reads); out = {mean, biased variance}.
 __global__ void __launch_bounds__(256) stats_reduce_kernel(const StatPartial* __restrict__ partials, double* __restrict__ out,
                                                            int ncb, int CB, int Cout, int ipb, int jn) {
   __shared__ double sh[3][256];
   const int n = blockIdx.x / ncb, cb = blockIdx.x % ncb;
   const int c = threadIdx.x % CB, j = threadIdx.x / CB;
-  const StatPartial* base = partials + (size_t)blockIdx.x * ipb * 4 * CB + c;
+  const StatPartial* base = partials + (size_t)blockIdx.x * ipb * CB + c;
   double cn = 0.0, cm = 0.0, cq = 0.0;
-  for (int p = j; p < ipb * 4; p += jn) {
+  for (int p = j; p < ipb; p += jn) {
     const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * CB);
     stat_merge<double>(cn, cm, cq, (double)v.x, (double)v.y, (double)v.z);
   }
@@ -995,7 +995,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       if (lane == 0) tc::mbar_arrive(acc_empty + 8 * slot);
       if (++slot == R) { slot = 0; phase ^= 1; }
     }
-    StatPartial* pout = p.partials + ((size_t)(blockIdx.x * p.G + g) * 4 + q) * CB;
+    // the four epilogue warps park their partials in this group's (now idle) activation ring: every MMA that read it and
+    // every copy that wrote it completed before the last acc_full; combined after the CTA-wide barrier below
+    StatPartial* pout = reinterpret_cast<StatPartial*>(smem + (size_t)g * SA * p.a_stage_bytes) + (size_t)q * CB;
     if constexpr (SMALL_CB) {
       // one transposing reduction for the whole CTA lifetime: Chan's merge of the rows' (count, mean, M2)
       const float n_row = valid ? cnt : 0.f;
@@ -1046,6 +1048,20 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
   tc::tc_fence_before();
   __syncthreads();
+  if constexpr (!TCONV) {
+    // one (count, mean, M2) partial per work item and channel: the four warps' partials merged in warp order
+    const int tl = (int)threadIdx.x - g * TPG;
+    if (!idle && !extra && tl < (int)CB) {
+      const StatPartial* pin = reinterpret_cast<const StatPartial*>(smem + (size_t)g * SA * p.a_stage_bytes) + tl;
+      float4 v = *reinterpret_cast<const float4*>(pin);
+#pragma unroll
+      for (int qq = 1; qq < 4; ++qq) {
+        const float4 u = *reinterpret_cast<const float4*>(pin + (size_t)qq * CB);
+        stat_merge<float>(v.x, v.y, v.z, u.x, u.y, u.z);
+      }
+      *reinterpret_cast<float4*>(p.partials + (size_t)(blockIdx.x * p.G + g) * CB + tl) = v;
+    }
+  }
   if (warp_abs == 1) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -1439,11 +1455,11 @@ inline int tc_plan_zb(const TcKParams& kp, int nb, int num_sms) {
   return ZB;
 }
 
-// StatPartial entries one launch of this layer writes (0 for a transposed conv): [item][4 epilogue warps][CB]
+// StatPartial entries one launch of this layer writes (0 for a transposed conv): [item][CB]
 inline size_t tc_partials_needed(const TcKParams& kp, int nb, int num_sms) {
   if (kp.tconv) return 0;
   const int ZB = tc_plan_zb(kp, nb, num_sms);
-  return (size_t)nb * kp.ncb * ((kp.D + ZB - 1) / ZB) * kp.tilesH * kp.tilesW * 4 * kp.CB;
+  return (size_t)nb * kp.ncb * ((kp.D + ZB - 1) / ZB) * kp.tilesH * kp.tilesW * kp.CB;
 }
 
 // sums: the layer's [n][Cout][2] fp64 statistics ({mean, variance} on return); partials: scratch of tc_partials_needed() entries

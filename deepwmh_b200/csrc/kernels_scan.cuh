@@ -7,24 +7,39 @@
 namespace dwmh {
 
 // ---------------------------------------------------------------------------------------------
-// a2  z-score.  Pass 1: {sum, sum of squares, count} over the mask in fp64 (12 B/voxel total with
-// pass 2: read, read, write).  128-bit coalesced loads, grid = multiple of the SM count.
+// a2  z-score: x = (x - mean) / (std + 1e-8) over the mask, population std, statistics in fp64 (12 B/voxel algorithmic:
+// read, read, write).  128-bit coalesced accesses, grid = multiple of the SM count.
 // mask_mode 0: all voxels; 1: seg[i] >= 0; 2: vol[i] != 0.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) zscore_reduce_kernel(const float* __restrict__ vol,
-                                                            const int8_t* __restrict__ seg, int64_t n,
-                                                            int mask_mode, double* __restrict__ acc) {
+__device__ __forceinline__ void zscore_stats(const double* acc, float& mean, float& denom) {
+  const double cnt = acc[2] > 0.0 ? acc[2] : 1.0;
+  const double m = acc[0] / cnt;
+  double var = acc[1] / cnt - m * m;
+  var = var > 0.0 ? var : 0.0;
+  mean = (float)m;
+  denom = (float)sqrt(var) + 1e-8f;     // fp32 add, as numpy does with a float32 scalar
+}
+
+// One cooperative launch for the whole z-score (volumes of DeepWMH's size are launch-latency bound: 29 MB is 4 us of
+// HBM time).  Every CTA reduces its share in fp64 and leaves {sum, sum of squares, count} in its own slot; a grid-wide
+// barrier (all CTAs are co-resident: cudaLaunchCooperativeKernel); every CTA then adds the slots in index order --
+// deterministic, no atomics on the data, no memset -- and applies the normalisation to the share it already read (the
+// second read is served by L2 for volumes below its 126 MB).  slots: [gridDim.x][3] doubles; barrier: one monotonically
+// increasing counter, `target` = its value once every CTA of THIS launch has arrived; out_stats (may be null) = the
+// totals for the host.
+__global__ void __launch_bounds__(256) zscore_fused_kernel(float* __restrict__ vol, const int8_t* __restrict__ seg, int64_t n, int mask_mode,
+                                                           double* __restrict__ slots, unsigned long long* __restrict__ barrier,
+                                                           unsigned long long target, double* __restrict__ out_stats) {
   double s = 0.0, ss = 0.0, cnt = 0.0;
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const float4* v4 = reinterpret_cast<const float4*>(vol);
+  float4* v4 = reinterpret_cast<float4*>(vol);
   const char4* s4 = reinterpret_cast<const char4*>(seg);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 v = ld_stream_f4(v4 + i);
+    const float4 v = v4[i];
     bool m0 = true, m1 = true, m2 = true, m3 = true;
     if (mask_mode == 1) { const char4 g = s4[i]; m0 = g.x >= 0; m1 = g.y >= 0; m2 = g.z >= 0; m3 = g.w >= 0; }
     else if (mask_mode == 2) { m0 = v.x != 0.f; m1 = v.y != 0.f; m2 = v.z != 0.f; m3 = v.w != 0.f; }
-    // fp32 partial of 4 then fp64: keeps the DFMA count at 1/4 of the element count
     const float a = m0 ? v.x : 0.f, b = m1 ? v.y : 0.f, c = m2 ? v.z : 0.f, d = m3 ? v.w : 0.f;
     s += (double)a + (double)b + (double)c + (double)d;
     ss += (double)a * a + (double)b * b + (double)c * c + (double)d * d;
@@ -39,33 +54,33 @@ __global__ void __launch_bounds__(256) zscore_reduce_kernel(const float* __restr
   }
   s = warp_sum_d(s); ss = warp_sum_d(ss); cnt = warp_sum_d(cnt);
   __shared__ double sh[3][8];
+  __shared__ double tot[3];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) { sh[0][w] = s; sh[1][w] = ss; sh[2][w] = cnt; }
   __syncthreads();
-  if (w == 0) {
-    s = l < 8 ? sh[0][l] : 0.0; ss = l < 8 ? sh[1][l] : 0.0; cnt = l < 8 ? sh[2][l] : 0.0;
-    s = warp_sum_d(s); ss = warp_sum_d(ss); cnt = warp_sum_d(cnt);
-    if (l == 0) { atomicAdd(acc + 0, s); atomicAdd(acc + 1, ss); atomicAdd(acc + 2, cnt); }
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) { sh[0][0] += sh[0][k]; sh[1][0] += sh[1][k]; sh[2][0] += sh[2][k]; }
+    double* my = slots + (size_t)blockIdx.x * 3;
+    my[0] = sh[0][0]; my[1] = sh[1][0]; my[2] = sh[2][0];
+    __threadfence();
+    atomicAdd(barrier, 1ull);
+    while (*reinterpret_cast<volatile unsigned long long*>(barrier) < target) { }
+    __threadfence();
   }
-}
-
-__device__ __forceinline__ void zscore_stats(const double* acc, float& mean, float& denom) {
-  const double cnt = acc[2] > 0.0 ? acc[2] : 1.0;
-  const double m = acc[0] / cnt;
-  double var = acc[1] / cnt - m * m;
-  var = var > 0.0 ? var : 0.0;
-  mean = (float)m;
-  denom = (float)sqrt(var) + 1e-8f;     // fp32 add, as numpy does with a float32 scalar
-}
-
-__global__ void __launch_bounds__(256) zscore_apply_kernel(float* __restrict__ vol, const int8_t* __restrict__ seg,
-                                                           int64_t n, int mask_mode, const double* __restrict__ acc) {
+  __syncthreads();
+  if (w == 0) {      // ordered total: lane l adds slots l, l + 32, ...; the 32 lane sums are combined in lane order
+    double a = 0.0, b = 0.0, c = 0.0;
+    const volatile double* vs = slots;
+    for (int k = l; k < (int)gridDim.x; k += 32) { a += vs[3 * k]; b += vs[3 * k + 1]; c += vs[3 * k + 2]; }
+    for (int k = 0; k < 32; ++k) {
+      const double ak = __shfl_sync(0xffffffffu, a, k), bk = __shfl_sync(0xffffffffu, b, k), ck = __shfl_sync(0xffffffffu, c, k);
+      if (l == 0) { if (k == 0) { tot[0] = ak; tot[1] = bk; tot[2] = ck; } else { tot[0] += ak; tot[1] += bk; tot[2] += ck; } }
+    }
+  }
+  __syncthreads();
+  if (out_stats && blockIdx.x == 0 && threadIdx.x < 3) out_stats[threadIdx.x] = tot[threadIdx.x];
   float mean, denom;
-  zscore_stats(acc, mean, denom);
-  const int64_t n4 = n >> 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  float4* v4 = reinterpret_cast<float4*>(vol);
-  const char4* s4 = reinterpret_cast<const char4*>(seg);
+  zscore_stats(tot, mean, denom);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 v = v4[i];
     bool m0 = true, m1 = true, m2 = true, m3 = true;
@@ -217,10 +232,27 @@ __global__ void __launch_bounds__(256) weight_map_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------
 // softmax_out may alias agg (in-place normalisation): neither is __restrict__ and every thread reads its own
 // elements before it writes them.
+template <bool VEC>      // VEC: V % 4 == 0 and every buffer 16-byte (seg: 4-byte) aligned
 __global__ void __launch_bounds__(256) finalize_kernel(const float* agg, const float* __restrict__ wgt,
                                                        float* softmax_out, uint8_t* __restrict__ seg,
                                                        int64_t V) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if constexpr (VEC) {
+    // 128-bit accesses (four voxels per thread and step): the pass is a pure stream, bound by bytes in flight
+    const int64_t V4 = V >> 2;
+    const float4* a0 = reinterpret_cast<const float4*>(agg); const float4* a1 = reinterpret_cast<const float4*>(agg + V);
+    const float4* w4 = reinterpret_cast<const float4*>(wgt);
+    float4* o0 = reinterpret_cast<float4*>(softmax_out); float4* o1 = softmax_out ? reinterpret_cast<float4*>(softmax_out + V) : nullptr;
+    uchar4* s4 = reinterpret_cast<uchar4*>(seg);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V4; i += stride) {
+      const float4 w = w4[i], x = a0[i], y = a1[i];
+      const float4 p0 = make_float4(x.x / w.x, x.y / w.y, x.z / w.z, x.w / w.w);
+      const float4 p1 = make_float4(y.x / w.x, y.y / w.y, y.z / w.z, y.w / w.w);
+      if (softmax_out) { o0[i] = p0; o1[i] = p1; }
+      if (seg) s4[i] = make_uchar4(p1.x > p0.x, p1.y > p0.y, p1.z > p0.z, p1.w > p0.w);
+    }
+    return;
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < V; i += stride) {
     const float w = wgt[i];
     const float p0 = agg[i] / w, p1 = agg[V + i] / w;
