@@ -86,6 +86,36 @@ def predict_case(trainer, plans: Dict, in_file: str, out_file: str, softmax_file
     preprocess.save_segmentation_nifti_from_softmax(trainer.network, softmax, out_file, props, 1, None, softmax_file, post3mm_file)
 
 
+def robex_fov_masking(case_names: List[str], image_folder: str, post_3mm_folder: str, post_fov_folder: str, robex_dir: str):
+    """deepwmh/main/predict.py:39-48,165-181: remove false positives outside the brain -- ROBEX (an external program,
+    `$ROBEX_DIR/runROBEX.sh <flair> <brain_out> <mask_out>`) skull-strips the pre-processed FLAIR and the 3 mm-cleaned label map
+    is multiplied with its mask: ((seg * mask) > 0.5) as float32 into 003_postproc_fov/<case>.nii.gz."""
+    sh, binary = os.path.join(robex_dir, "runROBEX.sh"), os.path.join(robex_dir, "ROBEX")
+    if not (os.path.isfile(sh) and os.path.isfile(binary)):
+        raise RuntimeError("Cannot find 'runROBEX.sh' and 'ROBEX' binary file in folder '%s', be sure to download and install ROBEX "
+                           "in your local machine and check the path given is correct." % robex_dir)
+    for case in case_names:
+        out_seg = os.path.join(post_fov_folder, case + ".nii.gz")
+        if os.path.isfile(out_seg):
+            try:
+                nifti.read_nifti(out_seg)
+                continue                                             # predict.py:41: skip what already loads
+            except Exception:
+                pass
+        flair = os.path.join(image_folder, case + "_0000.nii.gz")
+        brain_out = os.path.join(post_fov_folder, case + "_brain.nii.gz")
+        brain_mask = os.path.join(post_fov_folder, case + "_mask.nii.gz")
+        rc = subprocess.call([sh, flair, brain_out, brain_mask], stdout=subprocess.DEVNULL)
+        if rc != 0:
+            raise RuntimeError("runROBEX.sh failed with exit code %d for case %s" % (rc, case))
+        dat, hdr = nifti.read_nifti(os.path.join(post_3mm_folder, case + ".nii.gz"))
+        accept, _ = nifti.read_nifti(brain_mask)
+        for f in (brain_out, brain_mask):
+            if os.path.isfile(f):
+                os.remove(f)
+        nifti.write_nifti(out_seg, ((dat * accept) > 0.5).astype(np.float32), hdr, dtype=np.float32)
+
+
 def _worker(gpu: int, cases: List[Tuple[str, str, str, str]], model: Dict[str, str]):
     import torch
     import deepwmh_b200
@@ -171,12 +201,17 @@ def main(argv=None):
     for case, _, seg_path, post_path in work:                                  # predict.py:158-163 ran inside the workers
         if not (os.path.isfile(seg_path) and os.path.isfile(post_path)):
             raise RuntimeError('prediction of case "%s" did not produce its outputs.' % case)
+    final = post_3mm
     if os.environ.get("ROBEX_DIR"):
-        print("** ROBEX FOV masking is an external program (predict.py:165-181) and is not run by this entry point.")
+        robex_fov_masking(args.case_names, image_folder, post_3mm, post_fov, os.environ["ROBEX_DIR"])
+        final = post_fov
+    else:
+        print("** ROBEX_DIR is not set: the brain-mask step (predict.py:165-181, an external program) is skipped and "
+              "003_postproc_fov stays empty; the 3 mm-cleaned label maps are the result.")
     print("")
     print(">>> Prediction done.")
     print('>>> Raw/preprocessed images can be found in folder "%s".' % image_folder)
-    print('>>> Segmentation results can be found in folder "%s".' % post_3mm)
+    print('>>> Segmentation results can be found in folder "%s".' % final)
     print("")
     return 0
 

@@ -131,9 +131,18 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   constexpr int WPG = TC_WARPS_PER_GROUP;
   constexpr int TPG = WPG * 32;
   constexpr int NG = DUAL ? 2 : 1;
-  const bool extra = (FIRST || XFORM) && warp_abs >= NG * WPG;        // FIRST / XFORM kernels run one more warp per group
-  const int g = extra ? warp_abs - NG * WPG : warp_abs / WPG;
-  const int warp = extra ? 7 : warp_abs - g * WPG;      // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer, 7 slice fetcher (FIRST) / transform (XFORM)
+  // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer (+ transform in XFORM kernels), 7 slice fetcher (FIRST) / transform (XFORM)
+  bool extra = (FIRST || XFORM) && warp_abs >= NG * WPG;        // FIRST / XFORM kernels run one more warp per group
+  int g = extra ? warp_abs - NG * WPG : warp_abs / WPG;
+  int warp = extra ? 7 : warp_abs - g * WPG;
+  if constexpr (XFORM && DUAL) {
+    // 16 warps on 4 schedulers (warp_abs % 4): one transform warp, two epilogue warps and one light warp (producer or MMA
+    // issuer) per scheduler -- the default numbering puts two transform warps on scheduler 2 and one next to an MMA issuer.
+    // Epilogue warps keep covering the four TMEM lane quarters (warp_abs & 3) in both groups.
+    constexpr unsigned char kGroup[16] = {0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 1, 1};
+    constexpr unsigned char kRole[16] = {0, 1, 2, 3, 4, 5, 6, 0, 6, 2, 3, 4, 5, 7, 1, 7};
+    g = kGroup[warp_abs]; warp = kRole[warp_abs]; extra = warp == 7;
+  }
 
   int wi = blockIdx.x * p.G + g;
   const bool idle = wi >= p.total_items;
@@ -185,12 +194,16 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
   if (warp_abs == 1) tc::tmem_alloc(tc::smem_u32(tmem_ptr_smem), 512);
   if constexpr (XFORM) {
-    const int tl = threadIdx.x - g * TPG;          // each group: coefficients of ITS sample
-    if (tl < p.C0 && !idle) {
+    // each group: coefficients of ITS sample
+    for (int i = threadIdx.x; i < p.G * p.C0; i += blockDim.x) {
+      const int gg = i / p.C0, c_ = i - gg * p.C0;
+      const int item = min((int)blockIdx.x * p.G + gg, p.total_items - 1);
+      const int n_gg = item / (p.tilesW * p.tilesH * p.nzb * p.ncb);
       NormParams np{p.xf_sums, p.xf_gamma, p.xf_beta, p.xf_inv_count};
       float a_, b_;
-      norm_coeffs(np, n, p.C0, tl, a_, b_);
-      s_coef[tl] = a_; s_coef[64 + tl] = b_;
+      norm_coeffs(np, n_gg, p.C0, c_, a_, b_);
+      float* co = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)gg * 2 * 64;
+      co[c_] = a_; co[64 + c_] = b_;
     }
   }
   tc::tc_fence_before();
@@ -1050,16 +1063,17 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   __syncthreads();
   if constexpr (!TCONV) {
     // one (count, mean, M2) partial per work item and channel: the four warps' partials merged in warp order
-    const int tl = (int)threadIdx.x - g * TPG;
-    if (!idle && !extra && tl < (int)CB) {
-      const StatPartial* pin = reinterpret_cast<const StatPartial*>(smem + (size_t)g * SA * p.a_stage_bytes) + tl;
+    for (int i = threadIdx.x; i < p.G * (int)CB; i += blockDim.x) {
+      const int gg = i / (int)CB, c_ = i - gg * (int)CB;
+      if ((int)blockIdx.x * p.G + gg >= p.total_items) continue;          // idle second group of the last CTA
+      const StatPartial* pin = reinterpret_cast<const StatPartial*>(smem + (size_t)gg * SA * p.a_stage_bytes) + c_;
       float4 v = *reinterpret_cast<const float4*>(pin);
 #pragma unroll
       for (int qq = 1; qq < 4; ++qq) {
         const float4 u = *reinterpret_cast<const float4*>(pin + (size_t)qq * CB);
         stat_merge<float>(v.x, v.y, v.z, u.x, u.y, u.z);
       }
-      *reinterpret_cast<float4*>(p.partials + (size_t)(blockIdx.x * p.G + g) * CB + tl) = v;
+      *reinterpret_cast<float4*>(p.partials + (size_t)(blockIdx.x * p.G + gg) * CB + c_) = v;
     }
   }
   if (warp_abs == 1) tc::tmem_dealloc(tmem, 512);

@@ -166,9 +166,13 @@ class SegmentationNetwork:
         check(self._lib.dwmh_argmax2(self._ctx, _ptr(softmax), _ptr(seg), seg.numel(), self._st()))
         return seg
 
-    def normalize_(self, vol: torch.Tensor, seg: Optional[torch.Tensor] = None, mask_mode: int = 2):
-        """In-place z-score of a device fp32 volume (a2).  mask_mode: 0 all, 1 seg>=0, 2 vol!=0."""
+    def normalize_(self, vol: torch.Tensor, seg: Optional[torch.Tensor] = None, mask_mode: int = 2, return_stats: bool = True):
+        """In-place z-score of a device fp32 volume (a2).  mask_mode: 0 all, 1 seg>=0, 2 vol!=0.
+        return_stats: (mean, std, count) on the host -- this synchronises the stream; False keeps the call asynchronous."""
         assert vol.is_cuda and vol.dtype == torch.float32 and vol.is_contiguous()
+        if not return_stats:
+            check(self._lib.dwmh_zscore(self._ctx, _ptr(vol), _ptr(seg), vol.numel(), mask_mode, None, self._st()))
+            return None
         stats = (C.c_double * 3)()
         check(self._lib.dwmh_zscore(self._ctx, _ptr(vol), _ptr(seg), vol.numel(), mask_mode, stats, self._st()))
         return tuple(stats)

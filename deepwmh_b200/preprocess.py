@@ -181,7 +181,7 @@ def preprocess_test_case(network, plans: Dict, input_files: Sequence[str], force
         props["spacing_after_resampling"] = target_spacing
         props["use_nonzero_mask_for_norm"] = {0: use_mask}
         v = d[0].contiguous()
-        network.normalize_(v, sg[0].contiguous() if use_mask else None, 1 if use_mask else 0)
+        network.normalize_(v, sg[0].contiguous() if use_mask else None, 1 if use_mask else 0, return_stats=False)
         d = v[None]
     return d, sg, props
 

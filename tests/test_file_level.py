@@ -124,6 +124,29 @@ def test_cli_argument_errors(tmp_path):
         cli.main(["-i", img, "-n", "a", "-m", str(tmp_path), "-o", str(tmp_path / "o"), "--skip-bfc"])
 
 
+def test_robex_fov_masking_step(tmp_path):
+    """predict.py:39-48,165-181 with a stand-in runROBEX.sh (the real one is an external program): seg x brain mask."""
+    rng = np.random.default_rng(3)
+    img_dir, d3, dfov, rb = (tmp_path / n for n in ("img", "p3", "fov", "robex"))
+    for d in (img_dir, d3, dfov, rb):
+        d.mkdir()
+    hdr = nifti.default_header((10, 12, 8))
+    seg = (rng.random((10, 12, 8)) > 0.6).astype(np.float32)
+    mask = np.zeros((10, 12, 8), np.float32); mask[2:8, 3:9, 1:7] = 1
+    nifti.write_nifti(str(img_dir / "c1_0000.nii.gz"), rng.normal(size=(10, 12, 8)).astype(np.float32), hdr)
+    nifti.write_nifti(str(d3 / "c1.nii.gz"), seg, hdr, dtype=np.float32)
+    nifti.write_nifti(str(rb / "mask_src.nii.gz"), mask, hdr, dtype=np.float32)
+    with pytest.raises(RuntimeError, match="ROBEX"):
+        cli.robex_fov_masking(["c1"], str(img_dir), str(d3), str(dfov), str(rb))          # binaries missing
+    (rb / "ROBEX").write_text("")
+    (rb / "runROBEX.sh").write_text("#!/bin/sh\ncp \"$1\" \"$2\"\ncp %s \"$3\"\n" % (rb / "mask_src.nii.gz"))
+    os.chmod(str(rb / "runROBEX.sh"), 0o755)
+    cli.robex_fov_masking(["c1"], str(img_dir), str(d3), str(dfov), str(rb))
+    out, _ = nifti.read_nifti(str(dfov / "c1.nii.gz"))
+    assert np.array_equal(out, ((seg * mask) > 0.5).astype(np.float32))
+    assert sorted(os.listdir(str(dfov))) == ["c1.nii.gz"]                                   # temporaries removed
+
+
 @pytest.mark.gpu
 def test_cli_end_to_end_matches_oracle_pipeline(tmp_path):
     """DeepWMH_predict-style run on a tiny model: output tree, raw segmentation equal to the oracle run through the
