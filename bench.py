@@ -368,26 +368,33 @@ def run_b200(args):
                 tm["total_ms"] = ev_b[0].elapsed_time(ev_b[1])
                 tms.append(tm)
 
-        def agg_max(key):
-            v = max(t[key] for t in tms) if key == "total_ms" else sum(t[key] for t in tms) / len(tms)
+        def over_ranks(key, op):
+            v = sum(t[key] for t in tms) / len(tms)
             if world > 1:
                 tt = torch.tensor([v], device=dev, dtype=torch.float64)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(tt, op=op)
                 v = float(tt.item())
             return v
+
+        def agg_max(key):
+            return over_ranks(key, dist.ReduceOp.MAX)
         tot = sum(t["total_ms"] for t in tms) / len(tms)
         if world > 1:
             tt = torch.tensor([tot], device=dev, dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); tot = float(tt.item())
         tiles_ms, coll_ms, fin2_ms = agg_max("tiles_ms"), agg_max("collective_ms"), agg_max("finalize_ms")
+        tiles_min, coll_min = over_ranks("tiles_ms", dist.ReduceOp.MIN), over_ranks("collective_ms", dist.ReduceOp.MIN)
         big = {"shape": list(V2_SHAPE), "tiles": tms[0]["n_tiles"], "forwards": tms[0]["n_tiles"] * N_MIRRORS, "n_gpus": world,
                "s_per_volume": tot / 1e3, "volumes_per_s": 1e3 / tot, "tiles_ms_max_over_ranks": tiles_ms,
+               "tiles_ms_min_over_ranks": tiles_min,
                "collective": args.reduce if world > 1 else "none (1 GPU)", "collective_ms_max_over_ranks": coll_ms,
+               "collective_ms_min_over_ranks": coll_min,
                "collective_bytes": tms[0]["collective_bytes"] if world > 1 else 0,
-               "collective_GBps": (tms[0]["collective_bytes"] / 1e9 / (coll_ms / 1e3)) if (world > 1 and coll_ms > 0) else None,
+               "collective_GBps": (tms[0]["collective_bytes"] / 1e9 / (coll_min / 1e3)) if (world > 1 and coll_min > 0) else None,
                "finalize_ms": fin2_ms, "steps": args.big_steps,
                "tflops": tms[0]["n_tiles"] * N_MIRRORS * flops_fwd / 1e12 / (tot / 1e3),
                "note": "BASELINE config 4: timed from the normalised volume in HBM to seg + softmax on rank 0 (zeroing of the buffers, this rank's tiles, "
-                       "the collective, weight map + finalize); collective_ms includes waiting for the slowest rank"}
+                       "the collective, weight map + finalize).  collective_ms is measured per rank from the end of its own tiles: the MAX over ranks contains the wait "
+                       "for the slowest rank (tile-time skew between GPUs), the MIN is the rank that arrived last, i.e. the transfer itself; GB/s uses the MIN"}
         if world > 1:
             # agreement with the single-GPU result of the same volume (rank 0 computes it once, untimed)
             if rank == 0:
