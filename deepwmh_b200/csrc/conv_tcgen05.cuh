@@ -131,18 +131,32 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   constexpr int WPG = TC_WARPS_PER_GROUP;
   constexpr int TPG = WPG * 32;
   constexpr int NG = DUAL ? 2 : 1;
-  // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer (+ transform in XFORM kernels), 7 slice fetcher (FIRST) / transform (XFORM)
-  bool extra = (FIRST || XFORM) && warp_abs >= NG * WPG;        // FIRST / XFORM kernels run one more warp per group
-  int g = extra ? warp_abs - NG * WPG : warp_abs / WPG;
-  int warp = extra ? 7 : warp_abs - g * WPG;
-  if constexpr (XFORM && DUAL) {
-    // 16 warps on 4 schedulers (warp_abs % 4): one transform warp, two epilogue warps and one light warp (producer or MMA
-    // issuer) per scheduler -- the default numbering puts two transform warps on scheduler 2 and one next to an MMA issuer.
-    // Epilogue warps keep covering the four TMEM lane quarters (warp_abs & 3) in both groups.
-    constexpr unsigned char kGroup[16] = {0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 0, 1, 1};
-    constexpr unsigned char kRole[16] = {0, 1, 2, 3, 4, 5, 6, 0, 6, 2, 3, 4, 5, 7, 1, 7};
-    g = kGroup[warp_abs]; warp = kRole[warp_abs]; extra = warp == 7;
+  // role: 0 act producer, 1 MMA, 2..5 epilogue, 6 weight producer (+ transform in XFORM kernels), 7 slice fetcher (FIRST) / transform (XFORM).
+  // Warp numbering: the epilogue warps come first (TMEM lane quarter = warp_abs & 3 for both groups), the light producer warps next,
+  // the MMA issuers last and on different schedulers (warp_abs % 4); each scheduler gets two epilogue warps and, in the 16-warp
+  // kernels, one transform / builder warp.  (Measured against the original numbering -- issuer = warp 1 of each group, two transform
+  // warps on one scheduler -- and against issuer bookkeeping without tcgen05 fences / barrier peeks: all within +-1 % of 42.2 ms per
+  // 32-forward batch, so the ~500-1200 cycles per plane the issuer spends outside its MMA bursts and timed waits are not a
+  // scheduling artefact)
+  constexpr bool EXTRA = FIRST || XFORM;
+  int g, warp;
+  if constexpr (!DUAL) {
+    //            warp_abs:  0  1  2  3  4  5  6  7
+    constexpr unsigned char kRole7[7] = {2, 3, 4, 5, 0, 6, 1};
+    constexpr unsigned char kRole8[8] = {2, 3, 4, 5, 0, 6, 7, 1};
+    g = 0; warp = EXTRA ? kRole8[warp_abs] : kRole7[warp_abs];
+  } else if constexpr (!EXTRA) {
+    //            warp_abs:   0  1  2  3  4  5  6  7  8  9 10 11 12 13
+    constexpr unsigned char kGroup14[14] = {0, 0, 0, 0, 1, 1, 1, 1, 0, 1, 0, 1, 1, 0};
+    constexpr unsigned char kRole14[14] = {2, 3, 4, 5, 2, 3, 4, 5, 0, 0, 6, 6, 1, 1};
+    g = kGroup14[warp_abs]; warp = kRole14[warp_abs];
+  } else {
+    //            warp_abs:   0  1  2  3  4  5  6  7  8  9 10 11 12 13 14 15
+    constexpr unsigned char kGroup16[16] = {0, 0, 0, 0, 1, 1, 1, 1, 0, 1, 1, 1, 0, 0, 1, 0};
+    constexpr unsigned char kRole16[16] = {2, 3, 4, 5, 2, 3, 4, 5, 0, 0, 6, 7, 6, 7, 1, 1};
+    g = kGroup16[warp_abs]; warp = kRole16[warp_abs];
   }
+  const bool extra = warp == 7;
 
   int wi = blockIdx.x * p.G + g;
   const bool idle = wi >= p.total_items;
