@@ -91,7 +91,8 @@ class DwmhError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; DWMH_LIB_PATH selects another build of it (A/B timing of two kernel versions on one box)."""
+    return os.environ.get("DWMH_LIB_PATH") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = True) -> C.CDLL:

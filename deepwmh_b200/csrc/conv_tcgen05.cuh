@@ -68,6 +68,7 @@ struct TcKParams {
   const double* xf_sums; const float* xf_gamma; const float* xf_beta; double xf_inv_count; int xform; const void* xf_src;
   // FIRST kernels (Cin = 1 first conv): loader warps build an im2col operand from the fp32 volume / patches
   const float* fc_src; const SampleMeta* fc_metas; int fc_patch_mode, fc_SY, fc_SZ, first;
+  int stagger;        // cycles by which the second issuer of a dual-group CTA starts late (DWMH_TC_STAGGER: -1 = one burst, 0 = off)
   int G;              // work-item pipelines ("groups") per CTA: 2 = two tiles share the resident weights, each with 256 TMEM columns
   int total_items;
   unsigned long long* prof;   // dbg & 8: per-role wait/total cycle counters
@@ -194,7 +195,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const uint32_t bg = bar0 + (uint32_t)gg * nbar * 8u;
       for (uint32_t s_ = 0; s_ < SA; ++s_) { tc::mbar_init(bg + 8 * s_, 1); tc::mbar_init(bg + 8 * (SA + s_), 1); }
       for (uint32_t s_ = 0; s_ < R; ++s_) { tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * s_, 1); tc::mbar_init(bg + 16 * SA + 16 * NB + 8 * (R + s_), 4); }
-      for (uint32_t s_ = 0; s_ < SA; ++s_) tc::mbar_init(bg + 16 * SA + 16 * NB + 16 * R + 8 * s_, 2);
+      for (uint32_t s_ = 0; s_ < SA; ++s_) tc::mbar_init(bg + 16 * SA + 16 * NB + 16 * R + 8 * s_, XFORM ? 3 : 2);
     }
     if constexpr (FIRST)
       for (int gg = 0; gg < p.G; ++gg)
@@ -342,13 +343,15 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       if (lane == 0) { tc::mbar_arrive(a_ready + 8 * xf.idx); tc::mbar_arrive(s_empty + 8 * (j & 3)); }
       xf.advance(SA);
     }
-  } else if (XFORM && (warp == 6 || warp == 7)) {
-    // ---------------- norm-on-load: transform warps 6 and 7 (7 = extra warp of the group) -----------
-    // (plain stride-1 layer, 32-channel chunks, <= 64 input channels.)  The TMA producer (warp 0) lands the producer
-    // layer's RAW fp16 plane; these two warps apply InstanceNorm + LeakyReLU to it IN PLACE in shared memory (two
-    // 8-channel chunks each; out-of-image halo positions must stay exactly 0), publish it to the async proxy and
-    // signal a_ready.  TMA keeps several planes in flight without holding registers -- with register prefetch
-    // (LDG -> transform -> STS) one plane in flight per warp left the loaders bound by the HBM latency.
+  } else if (XFORM && (warp == 0 || warp == 6 || warp == 7)) {
+    // ---------------- norm-on-load: three loader / transform warps per group (roles 0, 6, 7) -----------
+    // (plain stride-1 layer, 32-channel chunks, <= 64 input channels.)  The input tensor is the producer layer's RAW fp16
+    // output.  Each lane streams its 16-byte slots of the haloed plane (one slot = 8 channels of one position) from global
+    // memory into registers -- two planes in flight per warp, the HBM / L2 latency is several plane-times long -- applies
+    // InstanceNorm + LeakyReLU of the producer, writes the result into the activation stage (positions outside the image stay
+    // exactly 0), publishes it to the async proxy and signals a_ready.  Shared-memory traffic per plane and group: one
+    // 11.5 KB write, against TMA write + load + store (34.5 KB) of an in-place transform -- in a kernel whose MMAs are bound
+    // by shared-memory operand reads, and where the load / store wavefronts of the in-place version collided with them.
     const bool leader = tc::elect_one();
     if (warp == 6 && g == 0 && leader) {
       const int ntile = p.nkc * p.tiles_per_kc;
@@ -358,66 +361,80 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
       }
     }
-    // Each warp owns two adjacent 8-channel chunks = one contiguous, 128-byte aligned run of 360 16-byte slots; lane l
-    // handles slots l, l + 32, ... so that every quarter-warp touches one aligned 128-byte line (chunk bases alone
-    // are only 64-byte aligned: per-chunk indexing cost two shared-memory wavefronts per access).
-    const int c8_0 = warp == 6 ? 0 : 2;            // chunks c8_0 (slots 0..179), c8_0 + 1 (slots 180..359)
-    constexpr int NPOS = TC_PH * TC_PW, NSLOT = 2 * NPOS, NIT = (NSLOT + 31) / 32;      // 180, 360, 12
-    uint32_t inside_bits = 0;
+    // slots of one stage: [4 chunks][180 positions]; loader wl owns slots [240 wl, 240 wl + 240) = parts of two adjacent chunks
+    constexpr int NPOS = TC_PH * TC_PW, PER = (4 * NPOS) / 3, NIT = (PER + 31) / 32;      // 180, 240, 8
+    const int wl = warp == 0 ? 0 : warp - 5;
+    const int cA = (PER * wl) / NPOS;                       // first chunk of this loader; its other chunk is cA + 1
+    const int HW = p.H * p.W;
+    const size_t V4 = (size_t)p.Din * HW;                   // 16-byte vectors per 8-channel chunk of one sample
+    uint32_t goff[NIT];
+    uint32_t inside_bits = 0, ch1_bits = 0, valid_bits = 0;
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
-      const int idx = lane + 32 * i;
-      const int pos = idx >= NPOS ? idx - NPOS : idx;
+      const int sl = lane + 32 * i, sg = PER * wl + sl;
+      const int c8 = sg / NPOS, pos = sg - c8 * NPOS;
       const int r = pos / TC_PW, c = pos - r * TC_PW;
-      if (idx < NSLOT && (unsigned)(h0 - 1 + r) < (unsigned)p.H && (unsigned)(w0 - 1 + c) < (unsigned)p.W) inside_bits |= 1u << i;
+      const int hh = h0 - 1 + r, ww = w0 - 1 + c;
+      const bool v = sl < PER, in = v && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
+      if (v) valid_bits |= 1u << i;
+      if (in) inside_bits |= 1u << i;
+      if (c8 != cA) ch1_bits |= 1u << i;
+      goff[i] = in ? (uint32_t)((size_t)c8 * V4 + (size_t)hh * p.W + ww) : 0u;
     }
-    const uint32_t full_bits = (lane < NSLOT - 32 * (NIT - 1)) ? (1u << NIT) - 1 : (1u << (NIT - 1)) - 1;
-    const bool all_inside = __all_sync(0xffffffffu, inside_bits == full_bits);
-    const bool second = lane >= NPOS - 32 * (NPOS / 32);          // in the mixed iteration (i = NPOS / 32) lanes >= 20 are in the second chunk
-    const int t_end = z_end - 1 - p.Jlo;
+    const uint4* src_n = reinterpret_cast<const uint4*>(p.xf_src) + (size_t)n * (p.C0 >> 3) * V4;
+    const int t_last = min(z_end - 1 - p.Jlo, p.Din - 1);
+    int t_ld = max(z_lo - p.Jhi, 0), kc_ld = 0;             // next (plane, channel chunk) to load
+    int kc_use = 0, cur_kc = -1;
     float a0[8], a1[8], b0[8], b1[8];
-    int cur_kc = -1;
     RingPos xf;
-    for (int t = z_lo - p.Jhi; t <= t_end; ++t) {
-      if (t < 0 || t >= p.Din) continue;
-      for (int kc = 0; kc < p.nkc; ++kc) {
-        DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_full + 8 * xf.idx, xf.phase, 8));
-        uint4* run = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes) + c8_0 * NPOS;
-        if (kc != cur_kc) {                                       // coefficients of the warp's two chunks, in registers
-          cur_kc = kc;
-          const float* co = s_coef + (kc * 4 + c8_0) * 8;
+    // Rolling prefetch with ONE register buffer: slot i of the next plane is requested right after slot i of the current plane
+    // has been taken out of its register, so every request has a whole plane-time to arrive (buffer 32 + coefficients 32
+    // registers; two full buffers did not fit the 128-register budget of the 512-thread CTA).
+    auto next_src = [&]() -> const uint4* {
+      if (t_ld > t_last) return nullptr;
+      const uint4* sp = src_n + (size_t)(kc_ld * 4) * V4 + (size_t)t_ld * HW;
+      if (++kc_ld == p.nkc) { kc_ld = 0; ++t_ld; }
+      return sp;
+    };
+    uint4 buf[NIT];
+    const uint4* sp = next_src();
+    if (sp) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { a0[j] = co[j]; a1[j] = co[8 + j]; b0[j] = co[64 + j]; b1[j] = co[72 + j]; }
-        }
+      for (int i = 0; i < NIT; ++i) buf[i] = ((inside_bits >> i) & 1u) ? ld_stream(sp + goff[i]) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    while (sp) {
+      const uint4* sp_next = next_src();
+      if (kc_use != cur_kc) {                                 // coefficients of the loader's two chunks, in registers
+        cur_kc = kc_use;
+        const float* co = s_coef + (kc_use * 4 + cA) * 8;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {                    // slots [0, 192) then [192, 360): 6 iterations each
-          uint4 raw[NIT / 2];
-#pragma unroll
-          for (int i = 0; i < NIT / 2; ++i) { const int idx = lane + 32 * (half * (NIT / 2) + i); if (idx < NSLOT) raw[i] = run[idx]; }
-#pragma unroll
-          for (int i = 0; i < NIT / 2; ++i) {
-            const int it = half * (NIT / 2) + i;
-            const int idx = lane + 32 * it;
-            if (idx < NSLOT) {
-              const bool ch1 = it > NPOS / 32 || (it == NPOS / 32 && second);
-              float f[8];
-              unpack8<T>(raw[i], f);
-              const bool inside = all_inside || ((inside_bits >> it) & 1u);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float ca = ch1 ? a1[j] : a0[j], cbv = ch1 ? b1[j] : b0[j];
-                const float z = fmaf(ca, f[j], cbv);
-                f[j] = inside ? fmaxf(z, 0.01f * z) : 0.f;
-              }
-              run[idx] = pack8<T>(f);
-            }
-          }
-        }
-        DWMH_TIMED_WAIT(w1_, tc::fence_proxy_async());
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
-        xf.advance(SA);
+        for (int j = 0; j < 8; ++j) { a0[j] = co[j]; a1[j] = co[8 + j]; b0[j] = co[64 + j]; b1[j] = co[72 + j]; }
       }
+      DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * xf.idx, xf.phase ^ 1, 8));
+      uint4* stage = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes) + PER * wl + lane;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const uint4 x = buf[i];
+        if (sp_next && ((inside_bits >> i) & 1u)) buf[i] = ld_stream(sp_next + goff[i]);
+        if ((valid_bits >> i) & 1u) {
+          const bool ch1 = (ch1_bits >> i) & 1u, inside = (inside_bits >> i) & 1u;
+          float f[8];
+          unpack8<T>(x, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float ca = ch1 ? a1[j] : a0[j], cbv = ch1 ? b1[j] : b0[j];
+            const float z = fmaf(ca, f[j], cbv);
+            f[j] = inside ? fmaxf(z, 0.01f * z) : 0.f;
+          }
+          stage[32 * i] = pack8<T>(f);
+        }
+      }
+      DWMH_TIMED_WAIT(w1_, tc::fence_proxy_async());
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
+      xf.advance(SA);
+      if (++kc_use == p.nkc) kc_use = 0;
+      sp = sp_next;
     }
   } else if (warp == 0) {
     // ---------------- activation producer: one TMA box per (input plane, channel chunk) -----------
@@ -517,6 +534,14 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const bool plain = p.nclass == 1 && p.Jlo == -1 && p.Jhi == 1;     // stride-1 3x3x3
     if (p.resident)
       for (int t = 0; t < p.nkc * p.tiles_per_kc; ++t) tc::mbar_wait(b_full + 8 * t, 0, 5);
+    if (DUAL && g == 1 && p.stagger > 0) {
+      // The two issuers of a CTA run identical work and otherwise stay in phase: both burst at once (each MMA then takes two
+      // slots of the shared tensor pipe) and both do their per-plane bookkeeping at once (pipe idle).  The lag between them is
+      // preserved from plane to plane, so group 1 starts one burst late and the bursts of one group cover the gaps of the other.
+      tc::mbar_wait(a_mma, 0, 4);                          // its first plane is there: the delay is not hidden behind a load
+      const long long t0_ = clock64();
+      while (clock64() - t0_ < (long long)p.stagger) { }
+    }
     RingPos a, b, fresh, done;
     bool b_peek = false;      // same for the weight ring
     bool a_peek = false;      // a_full of the CURRENT stage already observed complete (prefetched try_wait)
@@ -535,9 +560,12 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       if (plain && zo_hi - zo_lo == 2 && R >= 3 && 3 * CB <= 256 && fresh_from == zo_hi) {
         // ---- steady state (interior plane, exactly output plane t+1 is new).  The three accumulator slots are
         // contiguous except at the ring wrap, where every MMA is issued as two (the general path is ~5x slower per MMA,
-        // and 2 of every R planes straddle the wrap).
-        const uint32_t col = tmem + lo_slot * CB;
+        // and 2 of every R planes straddle the wrap).  The issuer STAYS in this loop for the whole run of interior planes:
+        // ncu's instruction-level samples showed it spending most of a plane in ~500 bookkeeping instructions of the outer
+        // loop (constant-bank reloads of the kernel parameters, path selection) with the MMA queue full only a third of the time.
         const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17), id3 = idesc0 | (((3 * CB) >> 3) << 17);
+        for (;;) {
+        const uint32_t col = tmem + lo_slot * CB;
         const bool wrap = lo_slot + 3 > R, wrapA = lo_slot + 2 == R;          // wrapA: slots R-2, R-1 | 0    else: R-1 | 0, 1
         const uint32_t idA = wrapA ? id2 : idesc1, idB = wrapA ? idesc1 : id2, offB = wrapA ? 2 * CB : CB;
         const uint32_t col1 = (lo_slot + 1 == R) ? tmem : col + CB, col2 = wrapA ? tmem : tmem + CB;      // slots lo+1, lo+2 when wrapping
@@ -625,6 +653,15 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         done.advance(R);
         ++next_done;
         __syncwarp();
+        // is input plane t + 1 interior as well?  (its outputs t .. t + 2 inside the block, the plane itself inside the volume)
+        if (t + 2 > z_end - 1 || t + 1 >= p.Din) break;
+        ++t;
+        lo_slot = (lo_slot + 1 == R) ? 0 : lo_slot + 1;           // the oldest live output plane is now t - 1
+        zo_lo_prev = t - 1;
+        DWMH_TIMED_WAIT(w1_, tc::mbar_wait(acc_empty + 8 * fresh.idx, fresh.phase ^ 1, 3));      // output plane t + 1 starts
+        fresh.advance(R);
+        ++next_fresh;
+        }
         continue;
       }
       if (p.nclass == 1 && p.Jlo == 0 && p.Jhi == 0 && p.tiles_per_kc == 9 && fresh_from == zo_hi) {
@@ -1505,6 +1542,14 @@ int tc_launch(TcLayer& t, int nb, double* sums, StatPartial* partials, int num_s
   const int ZB = tc_plan_zb(kp, nb, num_sms);
   kp.ZB = ZB; kp.nzb = (kp.D + ZB - 1) / ZB;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DWMH_TC_DEBUG"); dbg = e ? atoi(e) : 0; } kp.dbg = dbg; }
+  {
+    static int stg = -2;
+    if (stg == -2) { const char* e = getenv("DWMH_TC_STAGGER"); stg = e ? atoi(e) : 0; }
+    // one burst = the MMAs of one input plane at the shared-memory-bound rate
+    const int n3 = kp.jmax * kp.CB;
+    const int per_mma = std::max(n3 / 2, (4096 + 32 * n3) / 128);
+    kp.stagger = stg < 0 ? kp.nkc * 9 * (kp.KC / 16) * per_mma * (-stg) / 1 : stg;
+  }
   const long long items = (long long)nb * kp.ncb * kp.nzb * tiles;
   // both groups of a CTA must share the cout block whose weights are resident: pairs (2k, 2k+1) stay inside
   // one (n, cb) when the tiles x z-blocks count is even
