@@ -23,7 +23,7 @@ __all__ = [
     "ConvDropoutNormNonlin", "StackedConvLayers", "Generic_UNet", "InitWeights_He",
     "benchmark_plans", "build_network", "build_benchmark_network", "count_parameters",
     "compute_steps_for_sliding_window", "get_gaussian", "pad_nd_image",
-    "mirror_and_predict", "predict_3D_tiled", "predict_3D", "OracleTrainer",
+    "mirror_and_predict", "iter_predict_3D_tiled", "predict_3D_tiled", "predict_3D", "OracleTrainer",
     "zscore_nnunet", "zscore_deepwmh", "synthetic_flair", "hard_dice_binary",
     "parity_report", "forward_flops", "MIRROR_DIMS",
 ]
