@@ -70,6 +70,10 @@ __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   return r;
 }
 
+__device__ __forceinline__ void st_shared_128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // 256-bit global accesses (sm_100): two 16-byte voxel-chunks per instruction keep twice the bytes in flight per thread;
 // the pass is a pure stream and was bound by memory-level parallelism (2048 threads x 16 B per SM).
 __device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {

@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include "common.cuh"
 #include "tc_primitives.cuh"
@@ -66,6 +67,8 @@ struct TcKParams {
   // norm-on-load (XFORM kernels): the input tensor is the producer's RAW fp16 output; InstanceNorm + LeakyReLU of the
   // producer are applied to each landed plane in shared memory by the two producer warps before the MMA reads it
   const double* xf_sums; const float* xf_gamma; const float* xf_beta; double xf_inv_count; int xform; const void* xf_src;
+  int xf_cfence;      // norm-on-load: proxy fence executed by the MMA issuer after its acquire instead of by the loaders (DWMH_XF_CFENCE, default 1)
+  int xf_pf;          // norm-on-load: (plane, chunk) steps the TMA L2 prefetch runs ahead of the register loads (DWMH_XF_PREFETCH, 0 = off)
   // FIRST kernels (Cin = 1 first conv): loader warps build an im2col operand from the fp32 volume / patches
   const float* fc_src; const SampleMeta* fc_metas; int fc_patch_mode, fc_SY, fc_SZ, first;
   int stagger;        // cycles by which the second issuer of a dual-group CTA starts late (DWMH_TC_STAGGER: -1 = one burst, 0 = off)
@@ -179,8 +182,9 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const uint32_t a_ready = acc_empty + 8u * R;          // XFORM: plane transformed, ready for the MMA
   const uint32_t a_mma = (XFORM || FIRST) ? a_ready : a_full;      // what the MMA issuer waits on
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * nbar * p.G);
-  float* s_coef = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)g * 2 * 64;   // XFORM: a[64], b[64]
-  float* s_slice = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)p.G * 2 * 64 + (size_t)g * 4 * TC_FIRST_SLICE;   // FIRST: 4-slot ring of haloed input slices
+  const uint32_t aux_off = (p.off_bar + 8u * nbar * (uint32_t)p.G + 16u + 8u) & ~15u;      // 16-byte aligned (the loaders read coefficients as float4)
+  float* s_coef = reinterpret_cast<float*>(smem + aux_off) + (size_t)p.G * 2 * CB + (size_t)g * 2 * 64;   // XFORM: a[64], b[64]
+  float* s_slice = reinterpret_cast<float*>(smem + aux_off) + (size_t)p.G * 2 * CB + (size_t)p.G * 2 * 64 + (size_t)g * 4 * TC_FIRST_SLICE;   // FIRST: 4-slot ring of haloed input slices
   const uint32_t smem_a = smem_base + (uint32_t)g * SA * p.a_stage_bytes;          // this group's activation ring
   // UMMA shared-memory descriptors hold a 14-bit (address >> 4): descriptor arithmetic uses the masked offsets
   const uint32_t smem_a_d = smem_a & 0x3FFFFu, smem_b_d = (smem_base + p.off_b) & 0x3FFFFu;
@@ -217,7 +221,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       NormParams np{p.xf_sums, p.xf_gamma, p.xf_beta, p.xf_inv_count};
       float a_, b_;
       norm_coeffs(np, n_gg, p.C0, c_, a_, b_);
-      float* co = reinterpret_cast<float*>(smem + p.off_bar + 8 * nbar * p.G + 16) + (size_t)p.G * 2 * CB + (size_t)gg * 2 * 64;
+      float* co = reinterpret_cast<float*>(smem + aux_off) + (size_t)p.G * 2 * CB + (size_t)gg * 2 * 64;
       co[c_] = a_; co[64 + c_] = b_;
     }
   }
@@ -361,75 +365,104 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         tc::bulk_load(smem_base + p.off_b + t * p.b_tile_bytes, wsrc + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, b_full + 8 * t);
       }
     }
-    // slots of one stage: [4 chunks][180 positions]; loader wl owns slots [240 wl, 240 wl + 240) = parts of two adjacent chunks
-    constexpr int NPOS = TC_PH * TC_PW, PER = (4 * NPOS) / 3, NIT = (PER + 31) / 32;      // 180, 240, 8
+    // slots of one stage: [4 chunks][180 positions] of 16 bytes.  Every loader owns 60 positions of ALL four chunks: iteration i
+    // handles chunk i / 2, positions 60 wl + 32 (i & 1) + lane (the odd iterations are 28 lanes wide), so the chunk -- hence the
+    // coefficient set and the stage offset -- of an unrolled iteration is a compile-time constant and the three loaders run ONE
+    // copy of the loop.  What this code is tuned for (ncu source-level sampling):
+    //   * instruction footprint: a version with one specialised copy per loader ran slower although it executed 40 % fewer
+    //     instructions -- half of all samples of the loaders AND of the epilogue warps became instruction-fetch stalls
+    //     (the roles of this kernel run five different code regions at once);
+    //   * registers: 128 per thread in the 512-thread CTA, and a spill is an L2 round trip here (227 KB of the SM's 256 KB are
+    //     carved out as shared memory: the L1 cannot hold 512 stack frames).  Load buffer 32, coefficients of ONE chunk 16
+    //     (re-read from shared memory when the chunk changes, 4 x per plane), two position offsets;
+    //   * scoreboards: ptxas puts all loads of the buffer on ONE scoreboard, so a wait for any slot is a wait for every load
+    //     issued before it -- reloading slot by slot made each slot wait for the load issued one slot earlier.  The buffer is
+    //     therefore reloaded as one batch after the last slot has left its registers; it lands while the warp writes that
+    //     slot, signals, and waits for the next free stage.
+    constexpr int NPOS = TC_PH * TC_PW, NIT = 8, PPW = NPOS / 3;      // 180 positions, 60 per loader
     const int wl = warp == 0 ? 0 : warp - 5;
-    const int cA = (PER * wl) / NPOS;                       // first chunk of this loader; its other chunk is cA + 1
     const int HW = p.H * p.W;
     const size_t V4 = (size_t)p.Din * HW;                   // 16-byte vectors per 8-channel chunk of one sample
-    uint32_t goff[NIT];
-    uint32_t inside_bits = 0, ch1_bits = 0, valid_bits = 0;
+    uint32_t poff[2];
+    bool pin[2], pborder[2];
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int sl = lane + 32 * i, sg = PER * wl + sl;
-      const int c8 = sg / NPOS, pos = sg - c8 * NPOS;
+    for (int k = 0; k < 2; ++k) {
+      const int pos = PPW * wl + 32 * k + lane;
       const int r = pos / TC_PW, c = pos - r * TC_PW;
       const int hh = h0 - 1 + r, ww = w0 - 1 + c;
-      const bool v = sl < PER, in = v && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
-      if (v) valid_bits |= 1u << i;
-      if (in) inside_bits |= 1u << i;
-      if (c8 != cA) ch1_bits |= 1u << i;
-      goff[i] = in ? (uint32_t)((size_t)c8 * V4 + (size_t)hh * p.W + ww) : 0u;
+      const bool v = 32 * k + lane < PPW;
+      pin[k] = v && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
+      pborder[k] = v && !pin[k];                            // a slot of the stage that lies outside the image (stays 0)
+      poff[k] = pin[k] ? (uint32_t)(hh * p.W + ww) : 0u;
+    }
+    const uint32_t slot0 = (uint32_t)(PPW * wl + lane) * 16u;
+    // positions outside the image are written ONCE (zero) in every stage and never again: the tile, hence the set of such slots,
+    // is the same for every plane of the CTA (planes outside the volume are skipped altogether)
+    if (pborder[0] || pborder[1]) {
+      for (uint32_t s_ = 0; s_ < SA; ++s_)
+#pragma unroll
+        for (int i = 0; i < NIT; ++i)
+          if (pborder[i & 1]) st_shared_128(smem_a + s_ * p.a_stage_bytes + slot0 + ((i >> 1) * NPOS + 32 * (i & 1)) * 16, make_uint4(0u, 0u, 0u, 0u));
     }
     const uint4* src_n = reinterpret_cast<const uint4*>(p.xf_src) + (size_t)n * (p.C0 >> 3) * V4;
     const int t_last = min(z_end - 1 - p.Jlo, p.Din - 1);
     int t_ld = max(z_lo - p.Jhi, 0), kc_ld = 0;             // next (plane, channel chunk) to load
-    int kc_use = 0, cur_kc = -1;
-    float a0[8], a1[8], b0[8], b1[8];
-    RingPos xf;
-    // Rolling prefetch with ONE register buffer: slot i of the next plane is requested right after slot i of the current plane
-    // has been taken out of its register, so every request has a whole plane-time to arrive (buffer 32 + coefficients 32
-    // registers; two full buffers did not fit the 128-register budget of the 512-thread CTA).
     auto next_src = [&]() -> const uint4* {
       if (t_ld > t_last) return nullptr;
       const uint4* sp = src_n + (size_t)(kc_ld * 4) * V4 + (size_t)t_ld * HW;
       if (++kc_ld == p.nkc) { kc_ld = 0; ++t_ld; }
       return sp;
     };
+    // optional L2 prefetch (DWMH_XF_PREFETCH = steps ahead; measured neutral, default off): one lane of the group asks the TMA
+    // unit to pull the raw boxes of the coming (plane, chunk) steps into L2
+    int t_pf = t_ld, kc_pf = 0;
+    auto prefetch_next = [&]() {
+      if (t_pf > t_last) return;
+      if (wl == 0 && leader) tc::tma_prefetch_4d(&tmA0, (w0 - 1) * 8, h0 - 1, t_pf, n * (p.C0 >> 3) + kc_pf * 4);
+      if (++kc_pf == p.nkc) { kc_pf = 0; ++t_pf; }
+    };
+    for (int i = 0; i < p.xf_pf; ++i) prefetch_next();
+    int kc_use = 0;
+    RingPos xf;
     uint4 buf[NIT];
     const uint4* sp = next_src();
     if (sp) {
 #pragma unroll
-      for (int i = 0; i < NIT; ++i) buf[i] = ((inside_bits >> i) & 1u) ? ld_stream(sp + goff[i]) : make_uint4(0u, 0u, 0u, 0u);
+      for (int i = 0; i < NIT; ++i) buf[i] = pin[i & 1] ? ld_stream(sp + (size_t)(i >> 1) * V4 + poff[i & 1]) : make_uint4(0u, 0u, 0u, 0u);
     }
     while (sp) {
       const uint4* sp_next = next_src();
-      if (kc_use != cur_kc) {                                 // coefficients of the loader's two chunks, in registers
-        cur_kc = kc_use;
-        const float* co = s_coef + (kc_use * 4 + cA) * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { a0[j] = co[j]; a1[j] = co[8 + j]; b0[j] = co[64 + j]; b1[j] = co[72 + j]; }
-      }
+      if (p.xf_pf > 0) prefetch_next();
       DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * xf.idx, xf.phase ^ 1, 8));
-      uint4* stage = reinterpret_cast<uint4*>(smem + (size_t)g * SA * p.a_stage_bytes + (size_t)xf.idx * p.a_stage_bytes) + PER * wl + lane;
+      uint32_t stage = smem_a + xf.idx * p.a_stage_bytes + slot0;        // 32-bit shared address, kept opaque so that it stays in ONE
+      asm volatile("" : "+r"(stage));                                     // register (under pressure ptxas rebuilt it per slot from S2R / LDC chains)
+      const float4* co4 = reinterpret_cast<const float4*>(s_coef + kc_use * 32);
+      float ca[8], cb[8];
 #pragma unroll
       for (int i = 0; i < NIT; ++i) {
-        const uint4 x = buf[i];
-        if (sp_next && ((inside_bits >> i) & 1u)) buf[i] = ld_stream(sp_next + goff[i]);
-        if ((valid_bits >> i) & 1u) {
-          const bool ch1 = (ch1_bits >> i) & 1u, inside = (inside_bits >> i) & 1u;
-          float f[8];
-          unpack8<T>(x, f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float ca = ch1 ? a1[j] : a0[j], cbv = ch1 ? b1[j] : b0[j];
-            const float z = fmaf(ca, f[j], cbv);
-            f[j] = inside ? fmaxf(z, 0.01f * z) : 0.f;
-          }
-          stage[32 * i] = pack8<T>(f);
+        if ((i & 1) == 0) {                                   // coefficients of this iteration's chunk
+          const float4 a_lo = co4[i], a_hi = co4[i + 1], b_lo = co4[16 + i], b_hi = co4[17 + i];
+          ca[0] = a_lo.x; ca[1] = a_lo.y; ca[2] = a_lo.z; ca[3] = a_lo.w; ca[4] = a_hi.x; ca[5] = a_hi.y; ca[6] = a_hi.z; ca[7] = a_hi.w;
+          cb[0] = b_lo.x; cb[1] = b_lo.y; cb[2] = b_lo.z; cb[3] = b_lo.w; cb[4] = b_hi.x; cb[5] = b_hi.y; cb[6] = b_hi.z; cb[7] = b_hi.w;
         }
+        float f[8];
+        unpack8<T>(buf[i], f);
+        if (i == NIT - 1 && sp_next && !(p.dbg & 1)) {
+#pragma unroll
+          for (int q = 0; q < NIT; ++q)
+            if (pin[q & 1]) buf[q] = ld_stream(sp_next + (size_t)(q >> 1) * V4 + poff[q & 1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z = fmaf(ca[e], f[e], cb[e]);
+          f[e] = fmaxf(z, 0.01f * z);
+        }
+        if (pin[i & 1]) st_shared_128(stage + ((i >> 1) * NPOS + 32 * (i & 1)) * 16, pack8<T>(f));
       }
-      DWMH_TIMED_WAIT(w1_, tc::fence_proxy_async());
+      // generic-proxy stores -> async-proxy (UMMA) reads need a proxy fence on the causality path.  By default it sits on
+      // the consumer side: stores -> mbarrier arrive (release) -> issuer's wait (acquire) -> fence.proxy.async -> tcgen05.mma
+      // (p.xf_cfence = 0: executed here, a MEMBAR behind this warp's outstanding loads).
+      if (!p.xf_cfence) DWMH_TIMED_WAIT(w1_, tc::fence_proxy_async());
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
       xf.advance(SA);
@@ -572,6 +605,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int kc = 0; kc < p.nkc; ++kc) {
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           tc::tc_fence_after();
+          if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
           { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }   // result consumed after the burst
           const long long tb_ = prof_on ? clock64() : 0;
           if (!p.resident) {
@@ -671,6 +705,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int kc = 0; kc < p.nkc; ++kc) {
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           tc::tc_fence_after();
+          if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
           { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
           const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
           uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
@@ -720,6 +755,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           for (int kc = 0; kc < p.nkc; ++kc) {
             if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
             tc::tc_fence_after();
+            if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
             { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
             const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             const uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + tile0) * tile16;
@@ -778,6 +814,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           for (int kc = 0; kc < p.nkc; ++kc) {
             if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
             tc::tc_fence_after();
+            if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
             { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
             const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0) * tile16;
@@ -849,6 +886,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           a_peek = false;
           tc::tc_fence_after();
+          if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
           const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
           uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0) * tile16;
           for (int m = tapmask; m; m &= m - 1) {
@@ -1537,6 +1575,8 @@ int tc_launch(TcLayer& t, int nb, double* sums, StatPartial* partials, int num_s
     if (!fs) { if (err) *err = "first-conv launch without a source"; return 1; }
     kp.fc_src = fs->src; kp.fc_metas = fs->metas; kp.fc_patch_mode = fs->patch_mode; kp.fc_SY = fs->SY; kp.fc_SZ = fs->SZ;
   }
+  { static int cf = -1; if (cf < 0) { const char* e = getenv("DWMH_XF_CFENCE"); cf = e ? atoi(e) : 1; } kp.xf_cfence = cf; }
+  { static int pf = -1; if (pf < 0) { const char* e = getenv("DWMH_XF_PREFETCH"); pf = e ? std::max(0, std::min(16, atoi(e))) : 0; } kp.xf_pf = pf; }
   if (xf && t.xform_ok) { kp.xform = 1; kp.xf_sums = xf->sums; kp.xf_gamma = xf->gamma; kp.xf_beta = xf->beta; kp.xf_inv_count = xf->inv_count; kp.xf_src = xf->src; }
   const int tiles = kp.tilesH * kp.tilesW;
   const int ZB = tc_plan_zb(kp, nb, num_sms);
