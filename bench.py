@@ -42,7 +42,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.limit"
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
@@ -64,17 +64,22 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw, plim = [], None, set(), [], None
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
                 continue
+            try:
+                pw.append(float(r[2])); plim = float(r[7])
+            except Exception:
+                pass
             for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         busy = [s for s in sm if mx and s > 0.3 * mx] or sm
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw) if pw else None, "power_limit_w": plim}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -67,8 +67,6 @@ struct TcKParams {
   // norm-on-load (XFORM kernels): the input tensor is the producer's RAW fp16 output; InstanceNorm + LeakyReLU of the
   // producer are applied to each landed plane in shared memory by the two producer warps before the MMA reads it
   const double* xf_sums; const float* xf_gamma; const float* xf_beta; double xf_inv_count; int xform; const void* xf_src;
-  int xf_cfence;      // norm-on-load: proxy fence executed by the MMA issuer after its acquire instead of by the loaders (DWMH_XF_CFENCE, default 1)
-  int xf_pf;          // norm-on-load: (plane, chunk) steps the TMA L2 prefetch runs ahead of the register loads (DWMH_XF_PREFETCH, 0 = off)
   // FIRST kernels (Cin = 1 first conv): loader warps build an im2col operand from the fp32 volume / patches
   const float* fc_src; const SampleMeta* fc_metas; int fc_patch_mode, fc_SY, fc_SZ, first;
   int stagger;        // cycles by which the second issuer of a dual-group CTA starts late (DWMH_TC_STAGGER: -1 = one burst, 0 = off)
@@ -349,13 +347,12 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
   } else if (XFORM && (warp == 0 || warp == 6 || warp == 7)) {
     // ---------------- norm-on-load: three loader / transform warps per group (roles 0, 6, 7) -----------
-    // (plain stride-1 layer, 32-channel chunks, <= 64 input channels.)  The input tensor is the producer layer's RAW fp16
-    // output.  Each lane streams its 16-byte slots of the haloed plane (one slot = 8 channels of one position) from global
-    // memory into registers -- two planes in flight per warp, the HBM / L2 latency is several plane-times long -- applies
-    // InstanceNorm + LeakyReLU of the producer, writes the result into the activation stage (positions outside the image stay
-    // exactly 0), publishes it to the async proxy and signals a_ready.  Shared-memory traffic per plane and group: one
-    // 11.5 KB write, against TMA write + load + store (34.5 KB) of an in-place transform -- in a kernel whose MMAs are bound
-    // by shared-memory operand reads, and where the load / store wavefronts of the in-place version collided with them.
+    // (plain stride-1 layer, 32-channel chunks, <= 64 channels on load.)  The source is the producer layer's RAW fp16 output:
+    // each lane streams its 16-byte slots of the haloed plane (one slot = 8 channels of one position) from global memory into
+    // registers, applies InstanceNorm + LeakyReLU of the producer, writes the result into the activation stage (positions
+    // outside the image stay exactly 0) and signals a_ready.  Shared-memory traffic per plane and group: one 11.5 KB write,
+    // against TMA write + load + store (34.5 KB) of an in-place transform -- in a kernel whose MMAs are bound by shared-memory
+    // operand reads.
     const bool leader = tc::elect_one();
     if (warp == 6 && g == 0 && leader) {
       const int ntile = p.nkc * p.tiles_per_kc;
@@ -378,7 +375,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     //   * scoreboards: ptxas puts all loads of the buffer on ONE scoreboard, so a wait for any slot is a wait for every load
     //     issued before it -- reloading slot by slot made each slot wait for the load issued one slot earlier.  The buffer is
     //     therefore reloaded as one batch after the last slot has left its registers; it lands while the warp writes that
-    //     slot, signals, and waits for the next free stage.
+    //     slot, signals, and waits for the next free stage.  (A TMA prefetch of the coming boxes into L2 changed nothing.)
     constexpr int NPOS = TC_PH * TC_PW, NIT = 8, PPW = NPOS / 3;      // 180 positions, 60 per loader
     const int wl = warp == 0 ? 0 : warp - 5;
     const int HW = p.H * p.W;
@@ -405,69 +402,57 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (pborder[i & 1]) st_shared_128(smem_a + s_ * p.a_stage_bytes + slot0 + ((i >> 1) * NPOS + 32 * (i & 1)) * 16, make_uint4(0u, 0u, 0u, 0u));
     }
     const uint4* src_n = reinterpret_cast<const uint4*>(p.xf_src) + (size_t)n * (p.C0 >> 3) * V4;
-    const int t_last = min(z_end - 1 - p.Jlo, p.Din - 1);
-    int t_ld = max(z_lo - p.Jhi, 0), kc_ld = 0;             // next (plane, channel chunk) to load
+    const int t_last = min(z_end - 1 - p.Jlo, p.Din - 1), t_first = max(z_lo - p.Jhi, 0);
+    int t_ld = t_first, kc_ld = 0;                           // next (plane, channel chunk) of the raw source to load
     auto next_src = [&]() -> const uint4* {
       if (t_ld > t_last) return nullptr;
       const uint4* sp = src_n + (size_t)(kc_ld * 4) * V4 + (size_t)t_ld * HW;
       if (++kc_ld == p.nkc) { kc_ld = 0; ++t_ld; }
       return sp;
     };
-    // optional L2 prefetch (DWMH_XF_PREFETCH = steps ahead; measured neutral, default off): one lane of the group asks the TMA
-    // unit to pull the raw boxes of the coming (plane, chunk) steps into L2
-    int t_pf = t_ld, kc_pf = 0;
-    auto prefetch_next = [&]() {
-      if (t_pf > t_last) return;
-      if (wl == 0 && leader) tc::tma_prefetch_4d(&tmA0, (w0 - 1) * 8, h0 - 1, t_pf, n * (p.C0 >> 3) + kc_pf * 4);
-      if (++kc_pf == p.nkc) { kc_pf = 0; ++t_pf; }
-    };
-    for (int i = 0; i < p.xf_pf; ++i) prefetch_next();
-    int kc_use = 0;
     RingPos xf;
     uint4 buf[NIT];
-    const uint4* sp = next_src();
-    if (sp) {
+    {
+      const uint4* sp = next_src();
+      if (sp) {
 #pragma unroll
-      for (int i = 0; i < NIT; ++i) buf[i] = pin[i & 1] ? ld_stream(sp + (size_t)(i >> 1) * V4 + poff[i & 1]) : make_uint4(0u, 0u, 0u, 0u);
-    }
-    while (sp) {
-      const uint4* sp_next = next_src();
-      if (p.xf_pf > 0) prefetch_next();
-      DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * xf.idx, xf.phase ^ 1, 8));
-      uint32_t stage = smem_a + xf.idx * p.a_stage_bytes + slot0;        // 32-bit shared address, kept opaque so that it stays in ONE
-      asm volatile("" : "+r"(stage));                                     // register (under pressure ptxas rebuilt it per slot from S2R / LDC chains)
-      const float4* co4 = reinterpret_cast<const float4*>(s_coef + kc_use * 32);
-      float ca[8], cb[8];
-#pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        if ((i & 1) == 0) {                                   // coefficients of this iteration's chunk
-          const float4 a_lo = co4[i], a_hi = co4[i + 1], b_lo = co4[16 + i], b_hi = co4[17 + i];
-          ca[0] = a_lo.x; ca[1] = a_lo.y; ca[2] = a_lo.z; ca[3] = a_lo.w; ca[4] = a_hi.x; ca[5] = a_hi.y; ca[6] = a_hi.z; ca[7] = a_hi.w;
-          cb[0] = b_lo.x; cb[1] = b_lo.y; cb[2] = b_lo.z; cb[3] = b_lo.w; cb[4] = b_hi.x; cb[5] = b_hi.y; cb[6] = b_hi.z; cb[7] = b_hi.w;
-        }
-        float f[8];
-        unpack8<T>(buf[i], f);
-        if (i == NIT - 1 && sp_next && !(p.dbg & 1)) {
-#pragma unroll
-          for (int q = 0; q < NIT; ++q)
-            if (pin[q & 1]) buf[q] = ld_stream(sp_next + (size_t)(q >> 1) * V4 + poff[q & 1]);
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float z = fmaf(ca[e], f[e], cb[e]);
-          f[e] = fmaxf(z, 0.01f * z);
-        }
-        if (pin[i & 1]) st_shared_128(stage + ((i >> 1) * NPOS + 32 * (i & 1)) * 16, pack8<T>(f));
+        for (int i = 0; i < NIT; ++i) buf[i] = pin[i & 1] ? ld_stream(sp + (size_t)(i >> 1) * V4 + poff[i & 1]) : make_uint4(0u, 0u, 0u, 0u);
       }
-      // generic-proxy stores -> async-proxy (UMMA) reads need a proxy fence on the causality path.  By default it sits on
-      // the consumer side: stores -> mbarrier arrive (release) -> issuer's wait (acquire) -> fence.proxy.async -> tcgen05.mma
-      // (p.xf_cfence = 0: executed here, a MEMBAR behind this warp's outstanding loads).
-      if (!p.xf_cfence) DWMH_TIMED_WAIT(w1_, tc::fence_proxy_async());
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
-      xf.advance(SA);
-      if (++kc_use == p.nkc) kc_use = 0;
-      sp = sp_next;
+    }
+    for (int t_use = t_first; t_use <= t_last; ++t_use) {
+      for (int kc_use = 0; kc_use < p.nkc; ++kc_use) {
+        DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_empty + 8 * xf.idx, xf.phase ^ 1, 8));
+        const uint4* sp_next = next_src();
+        uint32_t stage = smem_a + xf.idx * p.a_stage_bytes + slot0;        // 32-bit shared address, kept opaque so that it stays in ONE
+        asm volatile("" : "+r"(stage));                                     // register (under pressure ptxas rebuilt it per slot from S2R / LDC chains)
+        const float4* co4 = reinterpret_cast<const float4*>(s_coef + kc_use * 32);
+        float ca[8], cb[8];
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          if ((i & 1) == 0) {                                   // coefficients of this iteration's chunk
+            const float4 a_lo = co4[i], a_hi = co4[i + 1], b_lo = co4[16 + i], b_hi = co4[17 + i];
+            ca[0] = a_lo.x; ca[1] = a_lo.y; ca[2] = a_lo.z; ca[3] = a_lo.w; ca[4] = a_hi.x; ca[5] = a_hi.y; ca[6] = a_hi.z; ca[7] = a_hi.w;
+            cb[0] = b_lo.x; cb[1] = b_lo.y; cb[2] = b_lo.z; cb[3] = b_lo.w; cb[4] = b_hi.x; cb[5] = b_hi.y; cb[6] = b_hi.z; cb[7] = b_hi.w;
+          }
+          float f[8];
+          unpack8<T>(buf[i], f);
+          if (i == NIT - 1 && sp_next && !(p.dbg & 1)) {
+#pragma unroll
+            for (int q = 0; q < NIT; ++q)
+              if (pin[q & 1]) buf[q] = ld_stream(sp_next + (size_t)(q >> 1) * V4 + poff[q & 1]);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float z = fmaf(ca[e], f[e], cb[e]);
+            f[e] = fmaxf(z, 0.01f * z);
+          }
+          if (pin[i & 1]) st_shared_128(stage + ((i >> 1) * NPOS + 32 * (i & 1)) * 16, pack8<T>(f));
+        }
+        DWMH_TIMED_WAIT(w1_, tc::fence_proxy_async());          // generic-proxy stores -> async-proxy (UMMA) reads
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(a_ready + 8 * xf.idx);
+        xf.advance(SA);
+      }
     }
   } else if (warp == 0) {
     // ---------------- activation producer: one TMA box per (input plane, channel chunk) -----------
@@ -605,7 +590,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int kc = 0; kc < p.nkc; ++kc) {
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           tc::tc_fence_after();
-          if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
           { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }   // result consumed after the burst
           const long long tb_ = prof_on ? clock64() : 0;
           if (!p.resident) {
@@ -705,7 +689,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         for (int kc = 0; kc < p.nkc; ++kc) {
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           tc::tc_fence_after();
-          if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
           { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
           const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
           uint32_t bl = b_lo_res + (uint32_t)kc * 9u * tile16;
@@ -755,7 +738,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           for (int kc = 0; kc < p.nkc; ++kc) {
             if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
             tc::tc_fence_after();
-            if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
             { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
             const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             const uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + tile0) * tile16;
@@ -814,7 +796,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           for (int kc = 0; kc < p.nkc; ++kc) {
             if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
             tc::tc_fence_after();
-            if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
             { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
             const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
             uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0) * tile16;
@@ -886,7 +867,6 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
           a_peek = false;
           tc::tc_fence_after();
-          if constexpr (XFORM) { if (p.xf_cfence) tc::fence_proxy_async(); }      // consumer-side proxy fence (see the loaders)
           const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
           uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + p.cls[c].tile0) * tile16;
           for (int m = tapmask; m; m &= m - 1) {
@@ -1175,7 +1155,7 @@ struct TcLayer {
   bool enabled = false;
   int ms0[6] = {0, 0, 0, 0, 0, 0}, ms1[6] = {0, 0, 0, 0, 0, 0};   // tensor-map specs {n, C, D, H, W, KC}; ms1[0] == 0 -> no second input
   bool map_bf16 = false;
-  bool xform_ok = false;          // layer shape supports norm-on-load (plain stride-1, one 32-channel chunk, resident weights)
+  bool xform_ok = false;          // layer shape supports norm-on-load of its (single) input: plain stride-1, 32-channel chunks, resident weights
   CUtensorMap tm0, tm1;
   void* wpack = nullptr;
   TcKParams kp{};
@@ -1575,8 +1555,6 @@ int tc_launch(TcLayer& t, int nb, double* sums, StatPartial* partials, int num_s
     if (!fs) { if (err) *err = "first-conv launch without a source"; return 1; }
     kp.fc_src = fs->src; kp.fc_metas = fs->metas; kp.fc_patch_mode = fs->patch_mode; kp.fc_SY = fs->SY; kp.fc_SZ = fs->SZ;
   }
-  { static int cf = -1; if (cf < 0) { const char* e = getenv("DWMH_XF_CFENCE"); cf = e ? atoi(e) : 1; } kp.xf_cfence = cf; }
-  { static int pf = -1; if (pf < 0) { const char* e = getenv("DWMH_XF_PREFETCH"); pf = e ? std::max(0, std::min(16, atoi(e))) : 0; } kp.xf_pf = pf; }
   if (xf && t.xform_ok) { kp.xform = 1; kp.xf_sums = xf->sums; kp.xf_gamma = xf->gamma; kp.xf_beta = xf->beta; kp.xf_inv_count = xf->inv_count; kp.xf_src = xf->src; }
   const int tiles = kp.tilesH * kp.tilesW;
   const int ZB = tc_plan_zb(kp, nb, num_sms);
