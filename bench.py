@@ -466,11 +466,11 @@ def run_b200(args):
         except Exception as e:
             inc = {"error": str(e)[:200]}
     # DRAM traffic per conv3_tc_kernel launch cannot be measured inside a timed run: it is the committed ncu pass of the same
-    # binary and command (tools/dram_traffic.py -> profiles/dram_traffic_r02.json, else round 1's file)
+    # binary and command (tools/dram_traffic.py -> profiles/dram_traffic_r02b.json, else the earlier files)
     ab, nl = conv_algorithmic_bytes(plans)
     alg_bytes = ab * args.max_batch / nl          # mean over the conv launches of one max_batch-forward batch
     traffic, traffic_src = None, None
-    for name in ("dram_traffic_r02.json", "dram_traffic_r01.json"):
+    for name in ("dram_traffic_r02b.json", "dram_traffic_r02.json", "dram_traffic_r01.json"):
         tpath = os.path.join(ROOT, "profiles", name)
         if os.path.isfile(tpath):
             try:
