@@ -76,6 +76,7 @@ SYMBOLS = {
     "dwmh_debug_layer_output": (C.c_int, [_P, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int32), _P]),
     "dwmh_num_layers": (C.c_int, [_P]),
     "dwmh_layer_kernel_kind": (C.c_int, [_P, C.c_int32]),
+    "dwmh_layer_norm_on_load": (C.c_int, [_P, C.c_int32]),
     "dwmh_set_force_generic": (C.c_int, [_P, C.c_int32]),
     "dwmh_get_counters": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "dwmh_set_stage_timing": (C.c_int, [_P, C.c_int32]),

@@ -259,6 +259,10 @@ extern "C" int dwmh_layer_kernel_kind(dwmh_ctx* c, int32_t i) {
   if (!c || i < 0 || i >= (int)c->layers.size()) return -1;
   return (c->layers[i].tc.enabled && !c->force_generic) ? 1 : 0;
 }
+extern "C" int dwmh_layer_norm_on_load(dwmh_ctx* c, int32_t i) {
+  if (!c || i < 0 || i >= (int)c->layers.size()) return -1;
+  return (c->layers[i].fused_norm && !c->force_generic) ? 1 : 0;
+}
 extern "C" int dwmh_set_force_generic(dwmh_ctx* c, int32_t on) { if (!c) return fail("null ctx"); c->force_generic = on != 0; return 0; }
 extern "C" int dwmh_get_counters(dwmh_ctx* c, int64_t* k, double* f) { if (!c) return fail("null ctx"); if (k) *k = c->launches; if (f) *f = c->conv_flops; return 0; }
 extern "C" int dwmh_set_stage_timing(dwmh_ctx* c, int32_t on) { if (!c) return fail("null ctx"); c->stage_timing = on != 0; return 0; }

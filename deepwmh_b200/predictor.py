@@ -253,6 +253,10 @@ class SegmentationNetwork:
     def layer_kernel_kind(self, index: int) -> int:
         return int(self._lib.dwmh_layer_kernel_kind(self._ctx, index))
 
+    def layer_norm_on_load(self, index: int) -> int:
+        """1 when the layer's InstanceNorm + LeakyReLU are applied by its consumer's loader warps (no separate pass)."""
+        return int(self._lib.dwmh_layer_norm_on_load(self._ctx, index))
+
     def set_force_generic(self, on: bool):
         check(self._lib.dwmh_set_force_generic(self._ctx, int(on)))
 

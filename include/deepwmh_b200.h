@@ -246,6 +246,9 @@ int dwmh_debug_layer_output(dwmh_ctx* ctx, int32_t layer_index, float* out_dev, 
 int dwmh_num_layers(dwmh_ctx* ctx);
 /* Kernel variant used by a layer: 0 = direct (CUDA cores), 1 = tcgen05 implicit GEMM. */
 int dwmh_layer_kernel_kind(dwmh_ctx* ctx, int32_t layer_index);
+/* 1 when the layer's InstanceNorm + LeakyReLU are applied by its consumer on load (no separate pass, the layer's buffer keeps
+ * the raw conv output), 0 otherwise, -1 for a bad index.  Valid after dwmh_commit_weights. */
+int dwmh_layer_norm_on_load(dwmh_ctx* ctx, int32_t layer_index);
 /* Force the generic kernels everywhere (1) or restore automatic selection (0) - for cross-checking. */
 int dwmh_set_force_generic(dwmh_ctx* ctx, int32_t on);
 /* Counters since creation: kernels launched by this library, conv FLOPs issued. */
