@@ -65,34 +65,35 @@ def test_tcgen05_layers_match_cuda_core_layers(cfg):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("base", [32, 64])
-def test_norm_on_load_layers_match_separate_norm_pass(base):
+@pytest.mark.parametrize("base,patch,nb", [(32, (72, 88, 44), 2), (64, (72, 88, 44), 2), (32, (72, 80, 40), 1)])
+def test_norm_on_load_layers_match_separate_norm_pass(base, patch, nb):
     """Layers whose InstanceNorm + LeakyReLU are applied by the consumer's loader warps (raw fp16 producer, one stride-1
     consumer) against the CUDA-core path with its separate norm pass: partial tiles in both in-plane axes (88 = 5.5 x 16,
     44 = 5.5 x 8: the loaders' zero-once border slots), 32-channel sources (one chunk step per plane) and 64-channel sources
-    (two steps per plane, coefficients re-read per chunk)."""
+    (two steps per plane, coefficients re-read per chunk); one sample of 72 x 80 x 40 gives 25 tiles x 15 z-blocks, an odd item
+    count, i.e. the single-group variant of the kernel (8 warps, its own role table)."""
     import deepwmh_b200
-    plans = small_plans(patch=(72, 88, 44), pools=((2, 2, 2),) * 2, base=base)
-    ps = (72, 88, 44)
+    plans = small_plans(patch=patch, pools=((2, 2, 2),) * 2, base=base)
+    ps = patch
     net = O.build_benchmark_network(0, plans)
-    tr = deepwmh_b200.nnUNetTrainerV2(plans, device=0, max_batch=2)
+    tr = deepwmh_b200.nnUNetTrainerV2(plans, device=0, max_batch=nb)
     tr.load_checkpoint_ram({"state_dict": net.state_dict()}, False)
     nw = tr.network
-    x = torch.randn(2, 1, *ps, generator=torch.Generator().manual_seed(3)).cuda()
+    x = torch.randn(nb, 1, *ps, generator=torch.Generator().manual_seed(3)).cuda()
     L = nw.num_layers()
     fused = [i for i in range(L) if nw.layer_norm_on_load(i) == 1]
     assert fused, "no layer of this plan is normalised on load"
     nw.set_force_generic(True)
     assert all(nw.layer_norm_on_load(i) == 0 for i in range(L))
     p_ref = nw.forward_patches(x).clone()
-    ref = [nw.layer_output(i, 2).clone() for i in range(L)]
+    ref = [nw.layer_output(i, nb).clone() for i in range(L)]
     nw.set_force_generic(False)
     p_tc = nw.forward_patches(x).clone()
     for i in range(L):
-        got = nw.layer_output(i, 2)
+        got = nw.layer_output(i, nb)
         assert torch.isfinite(got).all(), i
         rel = (got - ref[i]).abs().max().item() / (ref[i].abs().max().item() + 1e-9)
-        assert rel < 1e-2, (base, i, i in fused, rel)
+        assert rel < 1e-2, (base, patch, i, i in fused, rel)
     assert (p_tc - p_ref).abs().max().item() < 5e-3
     if all(nw.layer_kernel_kind(i) == 1 for i in range(L)):          # (a 64-channel first conv runs on the CUDA-core kernel: fp64 atomics)
         assert torch.equal(nw.forward_patches(x), p_tc)              # deterministic
