@@ -725,59 +725,66 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
       if (p.s222 && zo_lo == t && zo_hi == t + 1 && fresh_from == zo_hi && 2 * CB <= 256) {
         // ---- steady state of a stride-(2,2,2) conv, straight line: the 8 parity classes and their 1/2/2/4 in-plane taps
-        // are compile-time here (the tap loop below costs ~250 cycles per tap in loop / branch overhead alone, more than
-        // the two MMAs it issues).  Sub-plane t feeds output t (all classes) and t+1 (the four odd-depth classes, which
-        // come first: N = 2 CB); exactly output t+1 is new.
+        // are compile-time here (a tap LOOP costs more in loop / branch overhead than the two MMAs it issues -- tried twice:
+        // the generic loop at ~250 cycles per tap, and a compact purpose-built loop that ran enc1-a at 1.90 instead of 1.67 ms).
+        // Sub-plane t feeds output t (all classes) and t+1 (the four odd-depth classes, which come first: N = 2 CB); exactly
+        // output t+1 is new.  One specialised copy per (weights resident?, ring wrap?) so that the copy that runs -- resident,
+        // no wrap -- is contiguous code: with the four forms interleaved the ~900 instructions executed per plane were spread
+        // over 48 KB of SASS and the issuer, the bottleneck of these layers, stalled on instruction fetch at every branch target.
         const uint32_t col0 = tmem + lo_slot * CB, col1 = (lo_slot + 1 == R) ? tmem : col0 + CB;
-        const bool wrap = lo_slot + 1 == R;
         const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17);
+        auto s222_step = [&](auto res_c, auto wrap_c) {
+          constexpr bool RES = decltype(res_c)::value, WRAP = decltype(wrap_c)::value;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int cd = c >> 2, ph = (c >> 1) & 1, pw = c & 1;
-          const int tile0 = cd * 9 + (ph ? (pw ? 5 : 3) : (pw ? 1 : 0));
-          for (int kc = 0; kc < p.nkc; ++kc) {
-            if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
-            tc::tc_fence_after();
-            { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
-            const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
-            const uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + tile0) * tile16;
+          for (int c = 0; c < 8; ++c) {
+            const int cd = c >> 2, ph = (c >> 1) & 1, pw = c & 1;
+            const int tile0 = cd * 9 + (ph ? (pw ? 5 : 3) : (pw ? 1 : 0));
+            for (int kc = 0; kc < p.nkc; ++kc) {
+              if (!a_peek) DWMH_TIMED_WAIT(w0_, tc::mbar_wait(a_mma + 8 * a.idx, a.phase, 4));
+              tc::tc_fence_after();
+              { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }
+              const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
+              const uint32_t b_res = b_lo_res + (uint32_t)(kc * p.tiles_per_kc + tile0) * tile16;
 #pragma unroll
-            for (int iy = 0; iy < (ph ? 2 : 1); ++iy) {
+              for (int iy = 0; iy < (ph ? 2 : 1); ++iy) {
 #pragma unroll
-              for (int ix = 0; ix < (pw ? 2 : 1); ++ix) {
-                const int dy = ph ? iy : 1, dx = pw ? ix : 1, ti = iy * (pw ? 2 : 1) + ix;
-                uint32_t b_lo0;
-                if (p.resident) b_lo0 = b_res + ti * tile16;
-                else {
-                  if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
-                  tc::tc_fence_after();
-                  b_lo0 = ((smem_b_d + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
-                  { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
-                }
-                if (leader) {
+                for (int ix = 0; ix < (pw ? 2 : 1); ++ix) {
+                  const int dy = ph ? iy : 1, dx = pw ? ix : 1, ti = iy * (pw ? 2 : 1) + ix;
+                  uint32_t b_lo0;
+                  if constexpr (RES) b_lo0 = b_res + ti * tile16;
+                  else {
+                    if (!b_peek) DWMH_TIMED_WAIT(w1_, tc::mbar_wait(b_full + 8 * b.idx, b.phase, 6));
+                    tc::tc_fence_after();
+                    b_lo0 = ((smem_b_d + b.idx * p.b_tile_bytes) >> 4) | (b_lbo16 << 16);
+                    { const RingPos bn = b.next(NB); b_peek = tc::mbar_test_wait(b_full + 8 * bn.idx, bn.phase); }
+                  }
+                  if (leader) {
 #pragma unroll
-                  for (int kk = 0; kk < KSTEPS; ++kk) {
-                    const uint64_t adesc = tc_desc(a_hi, a_lo0 + dy * TC_PW + dx + kk * (2 * TC_PLANE_BYTES >> 4));
-                    const uint32_t bl = b_lo0 + kk * kstep_b;
-                    if (cd == 0) {
-                      const bool first_site = c == 0 && kk == 0;             // the step's first MMA overwrites output t+1
-                      if (wrap || (first_site && kc == 0)) {
-                        tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), idesc1, 1u);
-                        tc::umma_f16(col1, adesc, tc_desc(b_hi, bl + CB), idesc1, (first_site && kc == 0) ? 0u : 1u);
-                      } else tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), id2, 1u);
-                    } else tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), idesc1, 1u);
+                    for (int kk = 0; kk < KSTEPS; ++kk) {
+                      const uint64_t adesc = tc_desc(a_hi, a_lo0 + dy * TC_PW + dx + kk * (2 * TC_PLANE_BYTES >> 4));
+                      const uint32_t bl = b_lo0 + kk * kstep_b;
+                      if (cd == 0) {
+                        const bool first_site = c == 0 && kk == 0;             // the step's first MMA overwrites output t+1
+                        if (WRAP || (first_site && kc == 0)) {
+                          tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), idesc1, 1u);
+                          tc::umma_f16(col1, adesc, tc_desc(b_hi, bl + CB), idesc1, (first_site && kc == 0) ? 0u : 1u);
+                        } else tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), id2, 1u);
+                      } else tc::umma_f16(col0, adesc, tc_desc(b_hi, bl), idesc1, 1u);
+                    }
+                  }
+                  if constexpr (!RES) {
+                    if (elected) tc::umma_commit(b_empty + 8 * b.idx);
+                    b.advance(NB);
                   }
                 }
-                if (!p.resident) {
-                  if (elected) tc::umma_commit(b_empty + 8 * b.idx);
-                  b.advance(NB);
-                }
               }
+              if (elected) tc::umma_commit(a_empty + 8 * a.idx);
+              a.advance(SA);
             }
-            if (elected) tc::umma_commit(a_empty + 8 * a.idx);
-            a.advance(SA);
           }
-        }
+        };
+        if (p.resident) { if (lo_slot + 1 == R) s222_step(std::true_type{}, std::true_type{}); else s222_step(std::true_type{}, std::false_type{}); }
+        else { if (lo_slot + 1 == R) s222_step(std::false_type{}, std::true_type{}); else s222_step(std::false_type{}, std::false_type{}); }
         if (elected) tc::umma_commit(acc_full + 8 * done.idx);        // output plane t is complete
         done.advance(R);
         ++next_done;
