@@ -672,7 +672,11 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
       dim3 grid(std::max(gx, 1), nb * (L.cout >> 3));
       S2dParams sp{L.s2d, L.out_sp[0], L.out_sp[1], L.out_sp[2], L.s2d_s[0], L.s2d_s[1], L.s2d_s[2]};
       const double bytes = (double)nb * L.cout * V * ((L.raw32 ? 4 : 2) + 2 + (L.s2d ? 2 : 0));
-      DW_TRY(cls_timed(1, bytes, [&] { instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, norm_of(L), L.cout, V, sp); return 0; }));
+      const bool quad = sp.dst && sp.sw == 2 && (sp.W & 3) == 0;              // parity-split copy written with 256-bit stores
+      DW_TRY(cls_timed(1, bytes, [&] {
+        if (quad) instnorm_lrelu_kernel<T, true><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, norm_of(L), L.cout, V, sp);
+        else instnorm_lrelu_kernel<T><<<grid, 256, 0, st>>>(L.raw, L.raw32 ? 1 : 0, L.out, norm_of(L), L.cout, V, sp);
+        return 0; }));
       c->launches++;
     }
   }
