@@ -682,7 +682,8 @@ static int forward_impl(dwmh_ctx* c, const float* src, int patch_mode, int SX, i
   }
   // head: norm-on-load + 1x1x1 + softmax
   Layer& L = c->layers[c->last_conv];
-  dim3 grid((unsigned)((L.vout() + 255) / 256), nb);
+  const int64_t head_items = (L.cout == 32 && (L.vout() & 1) == 0) ? L.vout() / 2 : L.vout();      // two voxels per thread in the usual head
+  dim3 grid((unsigned)((head_items + 255) / 256), nb);
   DW_TRY(cls_timed(2, (double)nb * L.vout() * (2.0 * L.cout + 8.0), [&] {
     head_softmax_kernel<T><<<grid, 256, 4 * L.cout * sizeof(float), st>>>((const T*)L.out, norm_of(L), c->w_head_dev, c->probs, L.cout, L.vout()); return 0; }));
   c->launches++;
