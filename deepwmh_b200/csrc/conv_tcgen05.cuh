@@ -582,6 +582,10 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         // ncu's instruction-level samples showed it spending most of a plane in ~500 bookkeeping instructions of the outer
         // loop (constant-bank reloads of the kernel parameters, path selection) with the MMA queue full only a third of the time.
         const uint32_t id2 = idesc0 | (((2 * CB) >> 3) << 17), id3 = idesc0 | (((3 * CB) >> 3) << 17);
+        // one copy of the loop per weight mode (resident / streamed): with both inline the loop body spanned 33 KB of SASS for
+        // the ~240 instructions an iteration executes
+        auto steady = [&](auto res_c) {
+        constexpr bool RES = decltype(res_c)::value;
         for (;;) {
         const uint32_t col = tmem + lo_slot * CB;
         const bool wrap = lo_slot + 3 > R, wrapA = lo_slot + 2 == R;          // wrapA: slots R-2, R-1 | 0    else: R-1 | 0, 1
@@ -592,7 +596,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tc::tc_fence_after();
           { const RingPos an = a.next(SA); a_peek = tc::mbar_test_wait(a_mma + 8 * an.idx, an.phase); }   // result consumed after the burst
           const long long tb_ = prof_on ? clock64() : 0;
-          if (!p.resident) {
+          if constexpr (!RES) {
             // streamed weight tiles: one ring slot per tap, shared by the groups of the CTA
             const uint32_t a_lo0 = ((smem_a_d + a.idx * p.a_stage_bytes) >> 4) | a_lbo_field;
 #pragma unroll
@@ -680,6 +684,8 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         fresh.advance(R);
         ++next_fresh;
         }
+        };
+        if (p.resident) steady(std::true_type{}); else steady(std::false_type{});
         continue;
       }
       if (p.nclass == 1 && p.Jlo == 0 && p.Jhi == 0 && p.tiles_per_kc == 9 && fresh_from == zo_hi) {
