@@ -1546,6 +1546,26 @@ struct TcFirstSrc { const float* src; const SampleMeta* metas; int patch_mode, S
 // planes per z-block: split D until the grid fills the machine about twice
 inline int tc_plan_zb(const TcKParams& kp, int nb, int num_sms) {
   const int tiles = kp.tilesH * kp.tilesW;
+  static int model = -1;
+  if (model < 0) { const char* e = getenv("DWMH_TC_ZB_MODEL"); model = e ? atoi(e) : 1; }
+  if (model && !kp.first && !kp.tconv && kp.D >= 16) {
+    // 3-D convs on >= 16 planes: minimise waves x input planes per CTA (block + depth halo).  16^3 layers then run 128 CTAs of 18
+    // planes in one wave instead of 256 CTAs of 10 planes in two, dec3-a 1024 CTAs in 7 waves instead of 512 in 4 (3.46 rounded up):
+    // -6 % on dec3-a, -5..9 % on the 16^3 and the strided layers (profiles/ab_loader_r02b.txt).  The first conv, the transposed
+    // convs and the layers on <= 8 planes were faster with the fill rule below.
+    const int halo = kp.Jhi - kp.Jlo;
+    int best = kp.D; long long best_cost = -1;
+    for (int nzb = 1; nzb <= kp.D / 2; ++nzb) {
+      const int ZB = (kp.D + nzb - 1) / nzb;
+      if ((kp.D + ZB - 1) / ZB != nzb) continue;
+      const long long items = (long long)nb * kp.ncb * tiles * nzb;
+      const long long ctas = (items + kp.G - 1) / kp.G, waves = (ctas + num_sms - 1) / num_sms;
+      const long long cost = waves * (ZB + halo);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ZB; }
+    }
+    return best;
+  }
+  // split D until the grid fills the machine about twice
   int ZB = kp.D;
   while ((long long)nb * kp.ncb * tiles * ((kp.D + ZB - 1) / ZB) < 2LL * num_sms && ZB > 2) ZB = (ZB + 1) / 2;
   return ZB;
